@@ -1,0 +1,141 @@
+/* libbolt_cuda.so -- C ABI of the B200-native Boltzmann hot path.
+ *
+ * The reference (xzackli/Bolt.jl) has no FFI boundary: its "operator interface" for this
+ * path is the exported Julia function set (src/Bolt.jl:8-9).  This header defines the C ABI
+ * those functions bind through `ccall`; each entry point cites the reference function it
+ * replaces.  Everything crossing the boundary is plain C: pointers, sizes, POD structs.
+ *
+ * Dual numbers: a Julia `Vector{ForwardDiff.Dual{Tag,Float64,N}}` is bit-identical to a
+ * column-major (1+N) x len Float64 matrix, value first.  `nd = 1+N` is therefore the leading
+ * stride of every "dual-capable" array below; nd = 1 means plain Float64.
+ *
+ * Threading: a context is owned by one host thread; distinct contexts are independent.
+ * All calls are synchronous (they return after the context's stream has drained).
+ * Errors: 0 = success, negative = bolt_status; text via bolt_last_error().  Per-k solver
+ * outcomes are reported in status[] because the reference never inspects the ODE retcode
+ * (src/perturbations.jl:29-32).
+ */
+#ifndef BOLT_CUDA_H
+#define BOLT_CUDA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BOLT_ABI_VERSION 1
+
+/* order of the scalar block (each entry nd doubles, value first) */
+enum bolt_scalar {
+  BOLT_S_h = 0, BOLT_S_Omega_r, BOLT_S_Omega_b, BOLT_S_Omega_c, BOLT_S_A, BOLT_S_n,
+  BOLT_S_Y_p, BOLT_S_N_nu, BOLT_S_Sum_m_nu,          /* CosmoParams, src/Bolt.jl:56-66        */
+  BOLT_S_H0, BOLT_S_eta0, BOLT_S_rho_crit, BOLT_S_Omega_L, /* Background, src/background.jl:85-89 */
+  BOLT_NSCALARS
+};
+
+/* order of the cubic-B-spline coefficient tables (each (n_x+2) x nd doubles):
+ * bg.ℋ, bg.ℋ′, bg.ℋ′′, bg.η, bg.ρ₀ℳ (src/background.jl:95-101) and
+ * ih.τ, ih.τ′, ih.τ′′, ih.g̃, ih.g̃′, ih.g̃′′, ih.csb² (src/ionization/recfast.jl:7-19). */
+enum bolt_table {
+  BOLT_T_H = 0, BOLT_T_Hp, BOLT_T_Hpp, BOLT_T_eta, BOLT_T_rho0M,
+  BOLT_T_tau, BOLT_T_taup, BOLT_T_taupp, BOLT_T_g, BOLT_T_gp, BOLT_T_gpp, BOLT_T_csb2,
+  BOLT_NTABLES
+};
+
+typedef struct bolt_cosmo_desc {
+  int32_t abi_version;     /* BOLT_ABI_VERSION */
+  int32_t nd;              /* 1 + number of ForwardDiff partials */
+  int32_t n_x;             /* samples on bg.x_grid (tables hold n_x+2 coefficients) */
+  int32_t nq;              /* momentum quadrature nodes (bg.quad_pts) */
+  double  x0, dx;          /* bg.x_grid = x0 + dx*(0..n_x-1)  (src/background.jl:104) */
+  const double* scalars;   /* [BOLT_NSCALARS][nd] */
+  const double* quad_pts;  /* [nq]  Gauss-Legendre nodes on [-1,1] */
+  const double* quad_wts;  /* [nq] */
+  const double* tables;    /* [BOLT_NTABLES][n_x+2][nd] spline coefficients (itp.itp.coefs) */
+} bolt_cosmo_desc;
+
+enum bolt_mode { BOLT_MODE_ADAPTIVE = 0, BOLT_MODE_FIXED = 1 };
+
+/* options of one batch of k-mode solves: Hierarchy(...) truncations (src/perturbations.jl:20-21)
+ * and boltsolve keyword arguments (src/perturbations.jl:25). */
+typedef struct bolt_opts {
+  int32_t l_gamma, l_nu, l_mnu;  /* ℓᵧ, ℓ_ν, ℓ_mν */
+  int32_t mode;                  /* bolt_mode */
+  double  reltol, abstol;        /* adaptive mode */
+  double  fixed_dt;              /* fixed mode: step in x; (0 - x0)/fixed_dt steps are taken */
+  int64_t max_steps;             /* per k-mode; 0 = library default (1e6) */
+  int32_t ix_first;              /* first x_grid row for which sources / history are sampled */
+  int32_t reserved;
+} bolt_opts;
+
+enum bolt_status {
+  BOLT_OK = 0,
+  BOLT_ERR_ARG = -1, BOLT_ERR_CUDA = -2, BOLT_ERR_ALLOC = -3, BOLT_ERR_UNSUPPORTED = -4,
+  BOLT_ERR_NCCL = -5
+};
+/* per-k status[] values */
+enum bolt_k_status { BOLT_K_OK = 0, BOLT_K_MAXSTEPS = 1, BOLT_K_DT_UNDERFLOW = 2,
+                     BOLT_K_NONFINITE = 3, BOLT_K_RSA_TRIGGERED = 4 };
+
+typedef struct bolt_ctx bolt_ctx;       /* opaque: device, stream, scratch */
+typedef struct bolt_cosmo bolt_cosmo;   /* opaque: device-resident tables of one cosmology */
+
+/* lifecycle ------------------------------------------------------------------------------ */
+int  bolt_init(int device_ordinal, bolt_ctx** ctx);
+int  bolt_finalize(bolt_ctx* ctx);
+const char* bolt_last_error(const bolt_ctx* ctx);
+int  bolt_abi_version(void);
+
+/* Upload what Background(par) and IonizationHistory(𝕣, par, bg) computed on the host
+ * (src/background.jl:104-128, src/ionization/recfast.jl:674-726).  Copies; the caller keeps
+ * ownership of every host buffer. */
+int  bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* desc, bolt_cosmo** out);
+int  bolt_cosmo_free(bolt_ctx* ctx, bolt_cosmo* c);
+
+/* State dimension n = 2(ℓᵧ+1)+(ℓ_ν+1)+(ℓ_mν+1)nq+5 (src/perturbations.jl:281). */
+int  bolt_state_dim(int l_gamma, int l_nu, int l_mnu, int nq);
+
+/* boltsolve / source_grid / source_grid_P for a batch of k-modes
+ * (src/perturbations.jl:25-33, src/spectra.jl:6-42).  One solve per k feeds both sources.
+ * Any output pointer may be NULL.  Host buffers, caller-owned:
+ *   S_T, S_P   [nk][n_x][nd]   (i.e. Julia Matrix{T}(n_x, nk), column-major)
+ *   u_hist     [nk][n_x][n][nd]  solution sampled on bg.x_grid (what perturb(x) returns there)
+ *   u_final    [nk][n][nd]     perturb(0)
+ *   status     [nk], nsteps [nk] (accepted), nreject [nk] */
+int  bolt_solve(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
+                double* S_T, double* S_P, double* u_hist, double* u_final,
+                int32_t* status, int64_t* nsteps, int64_t* nreject);
+
+/* cltt / clte / clee for a vector of multipoles (src/spectra.jl:84-160).
+ * S_T,S_P are source grids on the coarse k grid k[nk] as returned by bolt_solve; the dense
+ * integration grid is quadratic_k(kd_min, kd_max, n_kd) (src/spectra.jl:60-63,133); ix_start is
+ * the 0-based index of the first x_grid point > -8 (src/spectra.jl:86).
+ * cl_* are [nell][nd]; any may be NULL. */
+int  bolt_project(bolt_ctx* ctx, const bolt_cosmo* c, const double* S_T, const double* S_P,
+                  const double* k, int nk, const int32_t* ell, int nell,
+                  double kd_min, double kd_max, int n_kd, int ix_start,
+                  double* cl_tt, double* cl_te, double* cl_ee);
+
+/* Fused source_grid + source_grid_P + cltt/clte/clee with the source grids kept in HBM
+ * (no host round trip).  Same meaning as bolt_solve followed by bolt_project. */
+int  bolt_spectra(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
+                  const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start,
+                  double* cl_tt, double* cl_te, double* cl_ee,
+                  int32_t* status, int64_t* nsteps);
+
+/* plin for a vector of k (src/spectra.jl:163-198; x = 0). pk is [nk][nd]. */
+int  bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
+               double* pk, int32_t* status, int64_t* nsteps);
+
+/* Timing of the last call's kernels on the context's stream (CUDA events), in ms:
+ * out[0] = hierarchy kernel, out[1] = Bessel tables, out[2] = projection kernel, out[3] = total.
+ * out[4..7] = launch counts of the same. */
+int  bolt_last_timing(const bolt_ctx* ctx, double* out8);
+
+/* Multi-GPU: join an NCCL communicator created by the host (one rank per process);
+ * afterwards bolt_spectra shards k-modes over ranks and all-reduces partial C_l. */
+int  bolt_comm_init(bolt_ctx* ctx, int rank, int nranks, const void* nccl_unique_id_128B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
