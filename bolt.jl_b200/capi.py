@@ -1,0 +1,150 @@
+"""ctypes binding of libbolt_cuda.so (include/bolt_cuda.h) -- the Python twin of julia/BoltCUDA.jl.
+
+There is no CPU fallback: loading fails loudly if the shared library is missing, and `Context()`
+raises if no CUDA device is usable.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libbolt_cuda.so")
+_LIB = None
+
+EXPORTS = ["bolt_abi_version", "bolt_init", "bolt_finalize", "bolt_last_error", "bolt_last_timing",
+           "bolt_cosmo_upload", "bolt_cosmo_free", "bolt_state_dim", "bolt_solve", "bolt_project",
+           "bolt_spectra", "bolt_plin"]
+
+
+class BoltError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise BoltError(f"{LIB_PATH} is missing: build it with `make -C {os.path.dirname(LIB_PATH)}` "
+                            "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp, dp, ip, lp = C.c_void_p, abi.c_double_p, abi.c_int32_p, abi.c_int64_p
+        L.bolt_abi_version.restype = C.c_int
+        L.bolt_init.argtypes = [C.c_int, C.POINTER(vp)]
+        L.bolt_finalize.argtypes = [vp]
+        L.bolt_last_error.argtypes = [vp]; L.bolt_last_error.restype = C.c_char_p
+        L.bolt_last_timing.argtypes = [vp, dp]
+        L.bolt_cosmo_upload.argtypes = [vp, C.POINTER(abi.CosmoDesc), C.POINTER(vp)]
+        L.bolt_cosmo_free.argtypes = [vp, vp]
+        L.bolt_state_dim.argtypes = [C.c_int] * 4
+        L.bolt_solve.argtypes = [vp, vp, dp, C.c_int, C.POINTER(abi.Opts), dp, dp, dp, dp, ip, lp, lp]
+        L.bolt_project.argtypes = [vp, vp, dp, dp, dp, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                   dp, dp, dp]
+        L.bolt_spectra.argtypes = [vp, vp, dp, C.c_int, C.POINTER(abi.Opts), ip, C.c_int, C.c_double, C.c_double,
+                                   C.c_int, C.c_int, dp, dp, dp, ip, lp]
+        L.bolt_plin.argtypes = [vp, vp, dp, C.c_int, C.POINTER(abi.Opts), dp, ip, lp]
+        _LIB = L
+    return _LIB
+
+
+class Context:
+    """bolt_ctx: one per (host thread x device)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().bolt_init(device, C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise BoltError(f"bolt_init(device={device}) failed with {rc}: no usable CUDA device "
+                            "(libbolt_cuda has no CPU fallback)")
+
+    def check(self, rc):
+        if rc != 0:
+            raise BoltError(f"libbolt_cuda error {rc}: {lib().bolt_last_error(self._h).decode()}")
+
+    def timing(self):
+        t = np.zeros(8)
+        lib().bolt_last_timing(self._h, abi.ptr(t))
+        return dict(hierarchy_ms=t[0], bessel_ms=t[1], project_ms=t[2], total_ms=t[3],
+                    hierarchy_launches=int(t[4]), bessel_launches=int(t[5]), project_launches=int(t[6]))
+
+    def close(self):
+        if self._h:
+            lib().bolt_finalize(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceCosmo:
+    """bolt_cosmo: the device-resident tables of one cosmology."""
+
+    def __init__(self, ctx, host_cosmo):
+        self.ctx, self.hc = ctx, host_cosmo
+        self._h = C.c_void_p()
+        ctx.check(lib().bolt_cosmo_upload(ctx._h, C.byref(host_cosmo.desc), C.byref(self._h)))
+
+    def close(self):
+        if self._h and self.ctx._h:
+            lib().bolt_cosmo_free(self.ctx._h, self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, k, opts, want=("S_T", "S_P")):
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        nk, n_x = len(k), self.hc.n_x
+        n = abi.state_dim(opts.l_gamma, opts.l_nu, opts.l_mnu, self.hc.nq)
+        out = {}
+        out["S_T"] = np.zeros((nk, n_x)) if "S_T" in want else None
+        out["S_P"] = np.zeros((nk, n_x)) if "S_P" in want else None
+        out["u_hist"] = np.zeros((nk, n_x, n)) if "u_hist" in want else None
+        out["u_final"] = np.zeros((nk, n)) if "u_final" in want else None
+        out["status"] = np.zeros(nk, dtype=np.int32)
+        out["nsteps"] = np.zeros(nk, dtype=np.int64)
+        out["nreject"] = np.zeros(nk, dtype=np.int64)
+        self.ctx.check(lib().bolt_solve(self.ctx._h, self._h, abi.ptr(k), nk, C.byref(opts), abi.ptr(out["S_T"]),
+                                        abi.ptr(out["S_P"]), abi.ptr(out["u_hist"]), abi.ptr(out["u_final"]),
+                                        abi.ptr(out["status"], abi.c_int32_p), abi.ptr(out["nsteps"], abi.c_int64_p),
+                                        abi.ptr(out["nreject"], abi.c_int64_p)))
+        return out
+
+    def project(self, S_T, S_P, k, ells, kd_min, kd_max, n_kd, ix_start):
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        ells = np.ascontiguousarray(ells, dtype=np.int32)
+        S_T = None if S_T is None else np.ascontiguousarray(S_T, dtype=np.float64)
+        S_P = None if S_P is None else np.ascontiguousarray(S_P, dtype=np.float64)
+        tt = np.zeros(len(ells)) if S_T is not None else None
+        ee = np.zeros(len(ells)) if S_P is not None else None
+        te = np.zeros(len(ells)) if (S_T is not None and S_P is not None) else None
+        self.ctx.check(lib().bolt_project(self.ctx._h, self._h, abi.ptr(S_T), abi.ptr(S_P), abi.ptr(k), len(k),
+                                          abi.ptr(ells, abi.c_int32_p), len(ells), kd_min, kd_max, n_kd, ix_start,
+                                          abi.ptr(tt), abi.ptr(te), abi.ptr(ee)))
+        return tt, te, ee
+
+    def spectra(self, k, opts, ells, kd_min, kd_max, n_kd, ix_start):
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        ells = np.ascontiguousarray(ells, dtype=np.int32)
+        tt, te, ee = np.zeros(len(ells)), np.zeros(len(ells)), np.zeros(len(ells))
+        st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
+        self.ctx.check(lib().bolt_spectra(self.ctx._h, self._h, abi.ptr(k), len(k), C.byref(opts),
+                                          abi.ptr(ells, abi.c_int32_p), len(ells), kd_min, kd_max, n_kd, ix_start,
+                                          abi.ptr(tt), abi.ptr(te), abi.ptr(ee), abi.ptr(st, abi.c_int32_p),
+                                          abi.ptr(ns, abi.c_int64_p)))
+        return tt, te, ee, st, ns
+
+    def plin(self, k, opts):
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        pk = np.zeros(len(k)); st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
+        self.ctx.check(lib().bolt_plin(self.ctx._h, self._h, abi.ptr(k), len(k), C.byref(opts), abi.ptr(pk),
+                                       abi.ptr(st, abi.c_int32_p), abi.ptr(ns, abi.c_int64_p)))
+        return pk, st, ns

@@ -1,0 +1,266 @@
+// libbolt_cuda.so -- C ABI (include/bolt_cuda.h) over the sm_100a kernels.
+// There is deliberately no CPU fallback: every entry point fails with BOLT_ERR_CUDA if no device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "hierarchy_kernel.cuh"
+#include "projection_kernel.cuh"
+
+using namespace bolt;
+
+struct bolt_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8];
+  std::string err;
+  double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int* d_counter = nullptr;
+};
+
+struct bolt_cosmo {
+  DevCosmo h;              // host copy (table pointers are device pointers)
+  DevCosmo* d = nullptr;   // device copy
+  double* d_tables = nullptr;
+};
+
+namespace {
+
+int fail(bolt_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+#define CUDA_OK(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, BOLT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t count) { n = count; return count ? cudaMalloc(&p, count * sizeof(T)) : cudaSuccess; }
+};
+
+bool g_const_init[64] = {false};
+
+int init_constants(bolt_ctx* ctx) {
+  if (g_const_init[ctx->device]) return BOLT_OK;
+  double rl[MAX_L + 1];
+  for (int l = 0; l <= MAX_L; l++) rl[l] = (double)l / (double)(2 * l + 1);
+  CUDA_OK(cudaMemcpyToSymbol(c_rl, rl, sizeof(rl)));
+  g_const_init[ctx->device] = true;
+  return BOLT_OK;
+}
+
+int check_opts(bolt_ctx* ctx, const bolt_cosmo* c, const bolt_opts* o) {
+  if (!o) return fail(ctx, BOLT_ERR_ARG, "opts is null");
+  if (o->l_gamma < 3 || o->l_nu < 3 || o->l_mnu < 3)
+    return fail(ctx, BOLT_ERR_ARG, "truncations must be >= 3 (source_function needs Theta_3, perturbations.jl:378)");
+  if (o->l_gamma > MAX_L || o->l_nu > MAX_L || o->l_mnu > MAX_L) return fail(ctx, BOLT_ERR_ARG, "truncation too large");
+  if (o->mode == BOLT_MODE_FIXED && !(o->fixed_dt > 0)) return fail(ctx, BOLT_ERR_ARG, "fixed_dt must be > 0");
+  if (o->mode == BOLT_MODE_ADAPTIVE && !(o->reltol > 0 && o->abstol > 0)) return fail(ctx, BOLT_ERR_ARG, "tolerances must be > 0");
+  if (c->h.nd != 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "dual partials (nd > 1) are not implemented in this build");
+  return BOLT_OK;
+}
+
+// Launch K1 on device buffers.
+int launch_hierarchy(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, const int* d_order, int nk, const bolt_opts* o,
+                     double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status, long long* d_nsteps,
+                     long long* d_nreject) {
+  SolveParams p;
+  p.cos = c->d; p.k = d_k; p.order = d_order; p.nk = nk;
+  p.L = o->l_gamma; p.Lnu = o->l_nu; p.Lm = o->l_mnu;
+  p.n = bolt_state_dim(p.L, p.Lnu, p.Lm, c->h.nq);
+  p.mode = o->mode; p.reltol = o->reltol; p.abstol = o->abstol; p.fixed_dt = o->fixed_dt;
+  p.max_steps = o->max_steps; p.ix_first = o->ix_first;
+  p.S_T = d_ST; p.S_P = d_SP; p.u_hist = d_hist; p.u_final = d_final;
+  p.status = d_status; p.nsteps = d_nsteps; p.nreject = d_nreject; p.counter = ctx->d_counter;
+  const size_t smem = (size_t)9 * p.n * sizeof(double);
+  CUDA_OK(cudaFuncSetAttribute(hierarchy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_OK(cudaFuncSetAttribute(hierarchy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int occ = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hierarchy_kernel, 32, smem));
+  if (occ < 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "state does not fit in shared memory");
+  const int grid = std::max(1, std::min(nk, occ * ctx->num_sms));
+  CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  hierarchy_kernel<<<grid, 32, smem, ctx->stream>>>(p);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->timing[4] += 1;
+  return BOLT_OK;
+}
+
+int upload_k_sorted(bolt_ctx* ctx, const double* k, int nk, DevBuf<double>& d_k, DevBuf<int>& d_order) {
+  std::vector<int> order(nk);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return k[a] > k[b]; });   // longest solves first
+  CUDA_OK(d_k.alloc(nk)); CUDA_OK(d_order.alloc(nk));
+  CUDA_OK(cudaMemcpyAsync(d_k.p, k, nk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(d_order.p, order.data(), nk * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));   // `order` is a local
+  return BOLT_OK;
+}
+
+int collect_timing(bolt_ctx* ctx) {
+  float ms = 0;
+  if (ctx->timing[4] > 0) { CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->timing[0] = ms; }
+  if (ctx->timing[5] > 0) { CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->timing[1] = ms; }
+  if (ctx->timing[6] > 0) { CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->timing[2] = ms; }
+  CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7])); ctx->timing[3] = ms;
+  return BOLT_OK;
+}
+void reset_timing(bolt_ctx* ctx) { for (int i = 0; i < 8; i++) ctx->timing[i] = 0; }
+
+}  // namespace
+
+extern "C" {
+
+int bolt_abi_version(void) { return BOLT_ABI_VERSION; }
+
+int bolt_state_dim(int l_gamma, int l_nu, int l_mnu, int nq) { return 2 * (l_gamma + 1) + (l_nu + 1) + (l_mnu + 1) * nq + 5; }
+
+int bolt_init(int device_ordinal, bolt_ctx** out) {
+  if (!out) return BOLT_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return BOLT_ERR_CUDA;   // no CPU fallback, by design
+  if (device_ordinal < 0 || device_ordinal >= ndev) return BOLT_ERR_ARG;
+  bolt_ctx* ctx = new bolt_ctx();
+  ctx->device = device_ordinal;
+  if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
+  for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
+  if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return BOLT_ERR_ALLOC; }
+  if (init_constants(ctx) != BOLT_OK) { delete ctx; return BOLT_ERR_CUDA; }
+  *out = ctx;
+  return BOLT_OK;
+}
+
+int bolt_finalize(bolt_ctx* ctx) {
+  if (!ctx) return BOLT_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& e : ctx->ev) cudaEventDestroy(e);
+  cudaFree(ctx->d_counter);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return BOLT_OK;
+}
+
+const char* bolt_last_error(const bolt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context (no CUDA device?)"; }
+
+int bolt_last_timing(const bolt_ctx* ctx, double* out8) {
+  if (!ctx || !out8) return BOLT_ERR_ARG;
+  for (int i = 0; i < 8; i++) out8[i] = ctx->timing[i];
+  return BOLT_OK;
+}
+
+int bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* d, bolt_cosmo** out) {
+  if (!ctx || !d || !out) return BOLT_ERR_ARG;
+  *out = nullptr;
+  if (d->abi_version != BOLT_ABI_VERSION) return fail(ctx, BOLT_ERR_ARG, "ABI version mismatch");
+  if (d->nq < 1 || d->nq > MAX_NQ) return fail(ctx, BOLT_ERR_ARG, "nq out of range (1..29)");
+  if (d->n_x < 4 || d->nd < 1) return fail(ctx, BOLT_ERR_ARG, "bad grid");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  bolt_cosmo* c = new bolt_cosmo();
+  DevCosmo& h = c->h;
+  h.n_x = d->n_x; h.nq = d->nq; h.nd = d->nd; h.x0 = d->x0; h.dx = d->dx; h.inv_dx = 1.0 / d->dx;
+  const int nd = d->nd, nc = d->n_x + 2;
+  for (int i = 0; i < BOLT_NSCALARS; i++) h.s[i] = d->scalars[(size_t)i * nd];
+  // value tables, contiguous [NTABLES][n_x+2]
+  std::vector<double> tabs((size_t)BOLT_NTABLES * nc);
+  for (int t = 0; t < BOLT_NTABLES; t++)
+    for (int i = 0; i < nc; i++) tabs[(size_t)t * nc + i] = d->tables[((size_t)t * nc + i) * nd];
+  if (cudaMalloc(&c->d_tables, tabs.size() * sizeof(double)) != cudaSuccess) { delete c; return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc tables"); }
+  cudaMemcpy(c->d_tables, tabs.data(), tabs.size() * sizeof(double), cudaMemcpyHostToDevice);
+  for (int t = 0; t < BOLT_NTABLES; t++) h.tab[t] = c->d_tables + (size_t)t * nc;
+  // momentum grid constants: T_nu (perturbations.jl:164), q_i (:165-166, util.jl:24-27), f0, dlnf0dlnq (background.jl:21-30)
+  const double N_nu = h.s[BOLT_S_N_nu], Om_r = h.s[BOLT_S_Omega_r], rho_crit = h.s[BOLT_S_rho_crit];
+  const double Tnu = std::pow(N_nu / 3.0, 0.25) * std::pow(4.0 / 11.0, 1.0 / 3.0) * std::pow(15.0 / (M_PI * M_PI) * rho_crit * Om_r, 0.25);
+  const double lqmi = std::log10(Tnu / 30.0), lqma = std::log10(Tnu * 30.0);
+  for (int i = 0; i < h.nq; i++) {
+    const double lq = lqmi + (lqma - lqmi) / 2.0 * (d->quad_pts[i] + 1.0);
+    const double q = std::pow(10.0, lq);
+    const double dxdq = (2.0 / (lqma - lqmi)) / (q * std::log(10.0));
+    const double f0 = 2.0 / std::pow(2.0 * M_PI, 3) / (std::exp(q / Tnu) + 1.0);
+    h.q[i] = q;
+    h.wq[i] = 4.0 * M_PI * q * q * (f0 / dxdq * d->quad_wts[i]);
+    h.df0[i] = -q / Tnu / (1.0 + std::exp(-q / Tnu));
+  }
+  h.Omega_nu = 7.0 * (2.0 / 3.0) * N_nu / 8.0 * std::pow(4.0 / 11.0, 4.0 / 3.0) * Om_r;
+  {  // eta(x_grid[end]) with the same spline arithmetic as the device
+    const double x_end = h.x0 + h.dx * (h.n_x - 1);
+    const double* ce = tabs.data() + (size_t)BOLT_T_eta * nc;
+    double t = (x_end - h.x0) / h.dx; int i = (int)std::floor(t); i = std::max(0, std::min(i, h.n_x - 2));
+    double dd = t - i, e = 1.0 - dd;
+    h.eta_end = ce[i] * (e * e * e / 6.0) + ce[i + 1] * (2.0 / 3.0 - dd * dd + dd * dd * dd / 2.0) +
+                ce[i + 2] * (2.0 / 3.0 - e * e + e * e * e / 2.0) + ce[i + 3] * (dd * dd * dd / 6.0);
+  }
+  if (cudaMalloc(&c->d, sizeof(DevCosmo)) != cudaSuccess) { cudaFree(c->d_tables); delete c; return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc cosmo"); }
+  cudaMemcpy(c->d, &h, sizeof(DevCosmo), cudaMemcpyHostToDevice);
+  *out = c;
+  return BOLT_OK;
+}
+
+int bolt_cosmo_free(bolt_ctx* ctx, bolt_cosmo* c) {
+  if (!c) return BOLT_OK;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(c->d); cudaFree(c->d_tables);
+  delete c;
+  return BOLT_OK;
+}
+
+int bolt_solve(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
+               double* S_T, double* S_P, double* u_hist, double* u_final,
+               int32_t* status, int64_t* nsteps, int64_t* nreject) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (!c || !k || nk < 1) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
+  int rc = check_opts(ctx, c, o); if (rc) return rc;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  reset_timing(ctx);
+  CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const int n = bolt_state_dim(o->l_gamma, o->l_nu, o->l_mnu, c->h.nq), n_x = c->h.n_x;
+  DevBuf<double> d_k, d_ST, d_SP, d_hist, d_final; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns, d_nr;
+  rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
+  if (S_T) { CUDA_OK(d_ST.alloc((size_t)nk * n_x)); CUDA_OK(cudaMemsetAsync(d_ST.p, 0, d_ST.n * 8, ctx->stream)); }
+  if (S_P) { CUDA_OK(d_SP.alloc((size_t)nk * n_x)); CUDA_OK(cudaMemsetAsync(d_SP.p, 0, d_SP.n * 8, ctx->stream)); }
+  if (u_hist) { CUDA_OK(d_hist.alloc((size_t)nk * n_x * n)); CUDA_OK(cudaMemsetAsync(d_hist.p, 0, d_hist.n * 8, ctx->stream)); }
+  if (u_final) CUDA_OK(d_final.alloc((size_t)nk * n));
+  CUDA_OK(d_status.alloc(nk)); CUDA_OK(d_ns.alloc(nk)); CUDA_OK(d_nr.alloc(nk));
+  rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, o, d_ST.p, d_SP.p, d_hist.p, d_final.p, d_status.p, d_ns.p, d_nr.p);
+  if (rc) return rc;
+  if (S_T) CUDA_OK(cudaMemcpyAsync(S_T, d_ST.p, d_ST.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (S_P) CUDA_OK(cudaMemcpyAsync(S_P, d_SP.p, d_SP.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (u_hist) CUDA_OK(cudaMemcpyAsync(u_hist, d_hist.p, d_hist.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (u_final) CUDA_OK(cudaMemcpyAsync(u_final, d_final.p, d_final.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, d_status.p, nk * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nsteps) CUDA_OK(cudaMemcpyAsync(nsteps, d_ns.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nreject) CUDA_OK(cudaMemcpyAsync(nreject, d_nr.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return collect_timing(ctx);
+}
+
+// --- not yet implemented in this build step -------------------------------------------------------
+int bolt_project(bolt_ctx* ctx, const bolt_cosmo*, const double*, const double*, const double*, int, const int32_t*, int,
+                 double, double, int, int, double*, double*, double*) { return fail(ctx, BOLT_ERR_UNSUPPORTED, "bolt_project: pending"); }
+int bolt_spectra(bolt_ctx* ctx, const bolt_cosmo*, const double*, int, const bolt_opts*, const int32_t*, int, double, double,
+                 int, int, double*, double*, double*, int32_t*, int64_t*) { return fail(ctx, BOLT_ERR_UNSUPPORTED, "bolt_spectra: pending"); }
+int bolt_plin(bolt_ctx* ctx, const bolt_cosmo*, const double*, int, const bolt_opts*, double*, int32_t*, int64_t*) {
+  return fail(ctx, BOLT_ERR_UNSUPPORTED, "bolt_plin: pending"); }
+
+}  // extern "C"

@@ -1,0 +1,738 @@
+// K1 -- batched Einstein-Boltzmann hierarchy solve, one warp per k-mode (sm_100a, FP64).
+//
+// Replaces, for a whole batch of wavenumbers at once:
+//   boltsolve                 src/perturbations.jl:25-33   (KenCarp4 ESDIRK, adaptive or fixed step)
+//   initial_conditions        src/perturbations.jl:274-338
+//   hierarchy!                src/perturbations.jl:161-271
+//   the sampling loop of source_grid / source_grid_P (src/spectra.jl:13-18, 32-37) with
+//   source_function / source_function_P (src/perturbations.jl:343-404), both from ONE solve.
+//
+// Layout.  The state of one mode lives in that warp's shared memory in the reference's own order
+// (unpack, perturbations.jl:114-125).  Lanes own "chains": lane q < nq owns the massive-neutrino
+// multipoles M[l*nq+q] (l = 0..l_mnu), lane nq owns Theta_l, lane nq+1 owns ThetaP_l, lane nq+2 owns
+// N_l.  The l+-1 couplings of a chain are therefore a sequential sweep inside one lane; the couplings
+// BETWEEN chains (Psi, Phi', Pi, v_b, the q-integrals rho_M, sigma_M) are warp shuffles.
+//
+// Implicit stages.  The hierarchy is linear, u' = A(x) u, so every ESDIRK stage is the linear system
+// (I - gamma*dt*A(x_s)) U = rhs.  A is block-tridiagonal over the chains plus a rank-4 coupling through
+// y = (Phi', Psi, Pi, v_b) and the five metric/matter scalars.  factor() runs a pivot-free downward
+// elimination of every chain (stable: off-diagonals have opposite signs and the diagonal is >= 1), carries
+// the y-dependence of rows l = 2,1,0 as 4-vectors, reduces them over the warp into a 4x4 system (partial
+// pivoting, registers).  solve() repeats the sweep for a right-hand side, solves the 4x4 system and
+// back-substitutes.  The factorisation costs O(n) like a solve, so it is redone at every stage abscissa
+// and the stage equations are solved exactly (the oracle does the same with a dense LU).
+#pragma once
+#include "common.cuh"
+
+namespace bolt {
+
+struct SolveParams {
+  const DevCosmo* cos;
+  const double* k;        // [nk]
+  const int* order;       // [nk] work order (largest k first)
+  int nk;
+  int L, Lnu, Lm, n;
+  int mode;
+  double reltol, abstol, fixed_dt;
+  long long max_steps;
+  int ix_first;
+  double* S_T;            // [nk][n_x] or null
+  double* S_P;            // [nk][n_x] or null
+  double* u_hist;         // [nk][n_x][n] or null
+  double* u_final;        // [nk][n] or null
+  int* status;            // [nk]
+  long long* nsteps;      // [nk]
+  long long* nreject;     // [nk]
+  int* counter;           // work queue head
+};
+
+__constant__ double c_rl[MAX_L + 1];   // l/(2l+1)
+
+// KenCarp4 implicit tableau (Kennedy & Carpenter 2003, ARK4(3)6L[2]SA-ESDIRK); SURVEY 8c.
+#define KC_GAMMA 0.25
+__device__ __constant__ double KC_C[6] = {0.0, 0.5, 83.0 / 250.0, 31.0 / 50.0, 17.0 / 20.0, 1.0};
+__device__ __constant__ double KC_A[6][5] = {
+    {0, 0, 0, 0, 0},
+    {1.0 / 4.0, 0, 0, 0, 0},
+    {8611.0 / 62500.0, -1743.0 / 31250.0, 0, 0, 0},
+    {5012029.0 / 34652500.0, -654441.0 / 2922500.0, 174375.0 / 388108.0, 0, 0},
+    {15267082809.0 / 155376265600.0, -71443401.0 / 120774400.0, 730878875.0 / 902184768.0, 2285395.0 / 8070912.0, 0},
+    {82889.0 / 524892.0, 0.0, 15625.0 / 83664.0, 69875.0 / 102672.0, -2260.0 / 8211.0}};
+// b - bhat (b = last row of A plus gamma)
+__device__ __constant__ double KC_E[6] = {
+    82889.0 / 524892.0 - 4586570599.0 / 29645900160.0, 0.0,
+    15625.0 / 83664.0 - 178811875.0 / 945068544.0, 69875.0 / 102672.0 - 814220225.0 / 1159782912.0,
+    -2260.0 / 8211.0 + 3700637.0 / 11593932.0, 0.25 - 61727.0 / 225920.0};
+
+enum ChainKind { CH_M = 0, CH_T = 1, CH_P = 2, CH_N = 3, CH_IDLE = 4 };
+
+// Everything a lane needs to know about the warp's mode and its own chain.
+struct Lane {
+  int lane, kind, base, stride, len;   // chain element l is at base + l*stride
+  int nq, L, iS, n, maxlen;
+  double k;
+  double q, df0, wq;                   // massive-neutrino lanes only
+};
+
+// Background / ionization quantities at one abscissa (warp-uniform) plus the lane's q/eps.
+struct Bg {
+  double x, a, H, eta, taup, taupp, csb2, Hp;
+  double kappa;     // k / H
+  double qe, eq;    // q/eps, eps/q for M lanes (1 otherwise)
+  double wPsi, wPhi;  // lane weights of chain rows 2 and 0 in the Psi and Phi' sums (see eval_bg)
+  double cPsi, gPhi, k2;  // 12 H0^2/(k^2 a^2), H0^2/(2 H^2), k^2/(3 H^2)
+  double R;
+};
+
+__device__ __forceinline__ void eval_bg(const DevCosmo& c, const Lane& ln, double x, Bg& b) {
+  // lanes 0..5 evaluate one table each, then broadcast (perturbations.jl:168,172)
+  const int which[6] = {BOLT_T_H, BOLT_T_eta, BOLT_T_taup, BOLT_T_taupp, BOLT_T_csb2, BOLT_T_Hp};
+  double v = 0.0;
+  if (ln.lane < 6) v = spline_eval(c.tab[which[ln.lane]], c.n_x, c.x0, c.dx, x);
+  b.x = x;
+  b.H = shfl_d(v, 0); b.eta = shfl_d(v, 1); b.taup = shfl_d(v, 2); b.taupp = shfl_d(v, 3);
+  b.csb2 = shfl_d(v, 4); b.Hp = shfl_d(v, 5);
+  b.a = exp(x);
+  b.kappa = ln.k / b.H;
+  const double Om_r = c.s[BOLT_S_Omega_r], Om_b = c.s[BOLT_S_Omega_b], rho_crit = c.s[BOLT_S_rho_crit];
+  const double H0 = c.s[BOLT_S_H0];
+  b.R = 4.0 * Om_r / (3.0 * Om_b * b.a);                       // :170
+  b.cPsi = 12.0 * H0 * H0 / (ln.k * ln.k) / (b.a * b.a);       // :184
+  b.gPhi = H0 * H0 / (2.0 * b.H * b.H);                        // :189
+  b.k2 = ln.k * ln.k / (3.0 * b.H * b.H);
+  b.qe = 1.0; b.eq = 1.0; b.wPsi = 0.0; b.wPhi = 0.0;
+  const double ia2 = 1.0 / (b.a * b.a);
+  if (ln.kind == CH_M) {
+    const double am = b.a * c.s[BOLT_S_Sum_m_nu];
+    const double eps = sqrt(ln.q * ln.q + am * am);            // :204
+    b.qe = ln.q / eps; b.eq = eps / ln.q;
+    // rho_M = sum wq*eps*M0, sigma_M = sum wq*(q^2/eps)*M2   (rho_sigma, :127-145)
+    b.wPhi = ln.wq * eps * ia2 / rho_crit;                     // a^-2 rho_M / rho_crit        (:193)
+    b.wPsi = ln.wq * (ln.q * ln.q / eps) / rho_crit * 0.25;    // sigma_M / rho_crit / 4       (:186)
+  } else if (ln.kind == CH_T) {
+    b.wPhi = 4.0 * Om_r * ia2; b.wPsi = Om_r;                  // :191, :184
+  } else if (ln.kind == CH_N) {
+    b.wPhi = 4.0 * c.Omega_nu * ia2; b.wPsi = c.Omega_nu;      // :192, :185
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Right-hand side rows (hierarchy!, perturbations.jl:161-271) for the lane's chain, rows 0..nrows-1,
+// reading chain values through `get(l)`.  Psi, Phi' and Pi are already known.
+// ---------------------------------------------------------------------------------------------------
+struct Metric { double Phi, delta, v, delta_b, v_b, Psi, dPhi, Pi; };
+
+template <class Get>
+__device__ __forceinline__ double rhs_row(const Lane& ln, const Bg& b, const Metric& m, int l, Get get) {
+  const bool photon = (ln.kind == CH_T || ln.kind == CH_P);
+  const double kq = b.kappa * b.qe;
+  if (l == ln.len - 1) {   // truncation rows :212, :243, :263-264
+    return kq * get(l - 1) - ((double)ln.len / (b.H * b.eta) - (photon ? b.taup : 0.0)) * get(l);
+  }
+  if (l == 0) {            // :207, :237, :248, :256
+    double r = -kq * get(1);
+    if (ln.kind == CH_M) r += m.dPhi * ln.df0;
+    else if (ln.kind == CH_P) r += b.taup * (get(0) - m.Pi * 0.5);
+    else r -= m.dPhi;
+    return r;
+  }
+  const double rl = c_rl[l];
+  double r = kq * (rl * get(l - 1) - (1.0 - rl) * get(l + 1));   // :208-210, :238-240, :249-252, :258-259
+  if (l == 1) {
+    if (ln.kind == CH_M) r -= b.kappa * (1.0 / 3.0) * b.eq * m.Psi * ln.df0;
+    else if (ln.kind != CH_P) r += b.kappa * (1.0 / 3.0) * m.Psi;
+    if (ln.kind == CH_T) r += b.taup * (m.v_b * (1.0 / 3.0));
+  }
+  if (photon) r += b.taup * (get(l) - (l == 2 ? m.Pi * 0.1 : 0.0));
+  return r;
+}
+
+// Psi, Phi', Pi from row-0 and row-2 chain values of every lane (perturbations.jl:182-194, 247)
+__device__ __forceinline__ void metric_from_chains(const Lane& ln, const Bg& b, double c0, double c2, Metric& m, const DevCosmo& c) {
+  const double sPsi = warp_sum(b.wPsi * c2);
+  const double sPhi = warp_sum(b.wPhi * c0);
+  double pi = 0.0;
+  if (ln.kind == CH_T) pi = c2; else if (ln.kind == CH_P) pi = c2 + c0;
+  m.Pi = warp_sum(pi);
+  m.Psi = -m.Phi - b.cPsi * sPsi;
+  m.dPhi = m.Psi - b.k2 * m.Phi + b.gPhi * (c.s[BOLT_S_Omega_c] / b.a * m.delta + c.s[BOLT_S_Omega_b] / b.a * m.delta_b + sPhi);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage matrix W = I - h*A(x):  factorisation state kept in registers between factor() and solve().
+// ---------------------------------------------------------------------------------------------------
+struct Factor {
+  double h, hk, dtau;           // gamma*dt, h*kappa*q/eps, -h*tau' (photon lanes)
+  double beta0[4], beta1[4], beta2[4];   // y-dependence of the lane's U_0, U_1, U_2
+  double lo1, lo2;              // sub-diagonals of rows 1, 2
+  double lu[4][4]; int perm[4]; // 4x4 border system, LU with partial pivoting
+  // constants needed again to build the border right-hand side
+  double hkap, vden;            // h*kappa, 1/(1+h)
+  double e4c;                   // -3 h tau' R
+};
+
+__device__ __forceinline__ void chain_coefs(const Lane& ln, const Factor& f, const Bg& b, int l, double& bd, double& up, double& lo) {
+  if (l == ln.len - 1) {
+    bd = 1.0 + f.h * (double)ln.len / (b.H * b.eta) + f.dtau; up = 0.0; lo = -f.hk;
+  } else {
+    const double rl = c_rl[l];
+    bd = 1.0 + ((l >= 1 || ln.kind == CH_P) ? f.dtau : 0.0);
+    up = f.hk * (1.0 - rl); lo = -f.hk * rl;
+  }
+}
+
+__device__ __forceinline__ void lu4_factor(Factor& f) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) f.perm[i] = i;
+#pragma unroll
+  for (int kx = 0; kx < 4; kx++) {
+    int p = kx; double best = fabs(f.lu[kx][kx]);
+#pragma unroll
+    for (int i = kx + 1; i < 4; i++) { double v = fabs(f.lu[i][kx]); if (v > best) { best = v; p = i; } }
+    if (p != kx) {
+#pragma unroll
+      for (int i = kx + 1; i < 4; i++) if (i == p) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { double t = f.lu[kx][j]; f.lu[kx][j] = f.lu[i][j]; f.lu[i][j] = t; }
+        int t = f.perm[kx]; f.perm[kx] = f.perm[i]; f.perm[i] = t;
+      }
+    }
+    const double ip = 1.0 / f.lu[kx][kx];
+#pragma unroll
+    for (int i = kx + 1; i < 4; i++) {
+      const double mlt = f.lu[i][kx] * ip; f.lu[i][kx] = mlt;
+#pragma unroll
+      for (int j = kx + 1; j < 4; j++) f.lu[i][j] -= mlt * f.lu[kx][j];
+    }
+  }
+}
+__device__ __forceinline__ void lu4_solve(const Factor& f, const double* rhs, double* y) {
+  double t[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (f.perm[i] == j) v = rhs[j];
+    t[i] = v;
+  }
+#pragma unroll
+  for (int i = 1; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < i; j++) t[i] -= f.lu[i][j] * t[j];
+#pragma unroll
+  for (int i = 3; i >= 0; i--) {
+#pragma unroll
+    for (int j = i + 1; j < 4; j++) t[i] -= f.lu[i][j] * t[j];
+    t[i] /= f.lu[i][i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) y[i] = t[i];
+}
+
+// Factor W = I - h A(x_s).  Writes the inverse chain pivots to ib[] (shared memory).
+__device__ __forceinline__ void factor(const DevCosmo& c, const Lane& ln, const Bg& b, double h, double* ib, Factor& f) {
+  const bool photon = (ln.kind == CH_T || ln.kind == CH_P);
+  f.h = h; f.hk = h * b.kappa * b.qe; f.dtau = photon ? -h * b.taup : 0.0;
+  f.hkap = h * b.kappa; f.vden = 1.0 / (1.0 + h);
+  f.e4c = -3.0 * h * b.taup * b.R;
+  double ibn = 0.0, lo_next = 0.0;
+  for (int l = ln.maxlen - 1; l >= 3; l--) {
+    if (l < ln.len) {
+      double bd, up, lo; chain_coefs(ln, f, b, l, bd, up, lo);
+      const double bp = bd - (up * ibn) * lo_next;
+      ibn = 1.0 / bp; lo_next = lo;
+      ib[ln.base + l * ln.stride] = ibn;
+    }
+  }
+  // rows 2, 1, 0 with the coupling to y = (Phi', Psi, Pi, v_b)
+  double C0[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0};
+  if (ln.kind == CH_M) { C0[0] = h * ln.df0; C1[1] = -f.hkap * (1.0 / 3.0) * b.eq * ln.df0; }
+  else if (ln.kind == CH_T) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); C1[3] = h * b.taup * (1.0 / 3.0); C2[2] = -h * b.taup * 0.1; }
+  else if (ln.kind == CH_P) { C0[2] = -h * b.taup * 0.5; C2[2] = -h * b.taup * 0.1; }
+  else if (ln.kind == CH_N) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); }
+  double ib2 = 0, ib1 = 0, ib0 = 0, m1 = 0, m0 = 0, lo1 = 0, lo2 = 0;
+  if (ln.kind != CH_IDLE) {
+    double bd, up, lo;
+    chain_coefs(ln, f, b, 2, bd, up, lo);
+    ib2 = 1.0 / (bd - (up * ibn) * lo_next); lo2 = lo;
+    chain_coefs(ln, f, b, 1, bd, up, lo);
+    m1 = up * ib2; ib1 = 1.0 / (bd - m1 * lo2); lo1 = lo;
+    chain_coefs(ln, f, b, 0, bd, up, lo);
+    m0 = up * ib1; ib0 = 1.0 / (bd - m0 * lo1);
+    ib[ln.base + 2 * ln.stride] = ib2; ib[ln.base + ln.stride] = ib1; ib[ln.base] = ib0;
+  }
+  f.lo1 = lo1; f.lo2 = lo2;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const double V2 = C2[j], V1 = C1[j] - m1 * V2, V0 = C0[j] - m0 * V1;
+    f.beta0[j] = V0 * ib0;
+    f.beta1[j] = (V1 - lo1 * f.beta0[j]) * ib1;
+    f.beta2[j] = (V2 - lo2 * f.beta1[j]) * ib2;
+  }
+  // reduce the y-dependence of the Psi, Phi', Pi sums and fetch Theta_1's from the Theta lane
+  double sPsi[4], sPhi[4], sPi[4], t1[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    sPsi[j] = warp_sum(b.wPsi * f.beta2[j]);
+    sPhi[j] = warp_sum(b.wPhi * f.beta0[j]);
+    double pi = 0.0;
+    if (ln.kind == CH_T) pi = f.beta2[j]; else if (ln.kind == CH_P) pi = f.beta2[j] + f.beta0[j];
+    sPi[j] = warp_sum(pi);
+    t1[j] = shfl_d(f.beta1[j], ln.nq);
+  }
+  // border equations E1..E4 in y (see DESIGN.md "stage system"); perturbations.jl:184-200
+  const double Oc = c.s[BOLT_S_Omega_c] / b.a, Ob = c.s[BOLT_S_Omega_b] / b.a;
+  const double hk = f.hkap;
+  // Phi = rPhi + h y0 ; v = (rv - hk y1)/(1+h) ; delta = rdelta + hk v - 3h y0 ; delta_b = rdb - 3h y0 + hk y3
+  const double dPhi_y[4] = {h, 0, 0, 0};
+  const double dDel_y[4] = {-3.0 * h, -hk * hk * f.vden, 0, 0};
+  const double dDb_y[4] = {-3.0 * h, 0, 0, hk};
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    f.lu[0][j] = dPhi_y[j] + b.cPsi * sPsi[j] + (j == 1 ? 1.0 : 0.0);                                   // E1: Psi + Phi + cPsi*SPsi = 0
+    f.lu[1][j] = (j == 0 ? 1.0 : 0.0) - (j == 1 ? 1.0 : 0.0) + b.k2 * dPhi_y[j]
+                 - b.gPhi * (Oc * dDel_y[j] + Ob * dDb_y[j] + sPhi[j]);                                // E2: Phi' definition
+    f.lu[2][j] = (j == 2 ? 1.0 : 0.0) - sPi[j];                                                         // E3: Pi definition
+    f.lu[3][j] = (j == 3 ? (1.0 + h - h * b.taup * b.R) : 0.0) + hk * ((j == 1 ? 1.0 : 0.0) + b.csb2 * dDb_y[j])
+                 + f.e4c * t1[j];                                                                       // E4: v_b equation
+  }
+  lu4_factor(f);
+}
+
+// Solve W U = r for the vector in r[] (shared, overwritten by U).  If zout != null also writes
+// zout = (U - rhs)/gamma with rhs recomputed by `rhs_of(idx)` (fused to avoid a second pass).
+template <class RhsOf>
+__device__ __forceinline__ void solve(const DevCosmo& c, const Lane& ln, const Bg& b, const Factor& f, const double* ib,
+                                      double* r, double* zout, RhsOf rhs_of) {
+  double ibn = 0.0, rn = 0.0;
+  for (int l = ln.maxlen - 1; l >= 3; l--) {
+    if (l < ln.len) {
+      const int idx = ln.base + l * ln.stride;
+      double v = r[idx];
+      if (l < ln.len - 1) v -= (f.hk * (1.0 - c_rl[l]) * ibn) * rn;
+      ibn = ib[idx]; rn = v; r[idx] = v;
+    }
+  }
+  double a0 = 0, a1 = 0, a2 = 0, ib0 = 0, ib1 = 0, ib2 = 0;
+  if (ln.kind != CH_IDLE) {
+    const int i0 = ln.base, i1 = ln.base + ln.stride, i2 = ln.base + 2 * ln.stride;
+    ib2 = ib[i2]; ib1 = ib[i1]; ib0 = ib[i0];
+    const double r2 = r[i2] - (f.hk * (1.0 - c_rl[2]) * ibn) * rn;
+    const double r1 = r[i1] - (f.hk * (1.0 - c_rl[1]) * ib2) * r2;
+    const double r0 = r[i0] - (f.hk * ib1) * r1;
+    a0 = r0 * ib0; a1 = (r1 - f.lo1 * a0) * ib1; a2 = (r2 - f.lo2 * a1) * ib2;
+  }
+  const double sPsi = warp_sum(b.wPsi * a2);
+  const double sPhi = warp_sum(b.wPhi * a0);
+  double pi = 0.0;
+  if (ln.kind == CH_T) pi = a2; else if (ln.kind == CH_P) pi = a2 + a0;
+  const double sPi = warp_sum(pi);
+  const double t1 = shfl_d(a1, ln.nq);
+  const int iS = ln.iS;
+  const double rPhi = r[iS], rdel = r[iS + 1], rv = r[iS + 2], rdb = r[iS + 3], rvb = r[iS + 4];
+  const double Oc = c.s[BOLT_S_Omega_c] / b.a, Ob = c.s[BOLT_S_Omega_b] / b.a;
+  const double hk = f.hkap, h = f.h;
+  const double vc = rv * f.vden, dc = rdel + hk * vc;
+  double rhs[4], y[4];
+  rhs[0] = -(rPhi + b.cPsi * sPsi);
+  rhs[1] = -(b.k2 * rPhi - b.gPhi * (Oc * dc + Ob * rdb + sPhi));
+  rhs[2] = sPi;
+  rhs[3] = -(hk * b.csb2 * rdb + f.e4c * t1 - rvb);
+  lu4_solve(f, rhs, y);
+  __syncwarp();
+  // scalars
+  {
+    const double Phi = rPhi + h * y[0];
+    const double v = vc - hk * f.vden * y[1];
+    const double del = rdel + hk * v - 3.0 * h * y[0];
+    const double db = rdb - 3.0 * h * y[0] + hk * y[3];
+    const double vb = y[3];
+    if (ln.lane == 0) {
+      if (zout) {
+        zout[iS] = (Phi - rhs_of(iS)) * (1.0 / KC_GAMMA); zout[iS + 1] = (del - rhs_of(iS + 1)) * (1.0 / KC_GAMMA);
+        zout[iS + 2] = (v - rhs_of(iS + 2)) * (1.0 / KC_GAMMA); zout[iS + 3] = (db - rhs_of(iS + 3)) * (1.0 / KC_GAMMA);
+        zout[iS + 4] = (vb - rhs_of(iS + 4)) * (1.0 / KC_GAMMA);
+      }
+      r[iS] = Phi; r[iS + 1] = del; r[iS + 2] = v; r[iS + 3] = db; r[iS + 4] = vb;
+    }
+  }
+  if (ln.kind != CH_IDLE) {
+    double U0 = a0, U1 = a1, U2 = a2;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { U0 += f.beta0[j] * y[j]; U1 += f.beta1[j] * y[j]; U2 += f.beta2[j] * y[j]; }
+    const int i0 = ln.base, i1 = ln.base + ln.stride, i2 = ln.base + 2 * ln.stride;
+    if (zout) {
+      zout[i0] = (U0 - rhs_of(i0)) * (1.0 / KC_GAMMA); zout[i1] = (U1 - rhs_of(i1)) * (1.0 / KC_GAMMA);
+      zout[i2] = (U2 - rhs_of(i2)) * (1.0 / KC_GAMMA);
+    }
+    r[i0] = U0; r[i1] = U1; r[i2] = U2;
+    double Up = U2;
+    for (int l = 3; l < ln.len; l++) {
+      const int idx = ln.base + l * ln.stride;
+      const double lo = (l == ln.len - 1) ? -f.hk : -f.hk * c_rl[l];
+      const double U = (r[idx] - lo * Up) * ib[idx];
+      if (zout) zout[idx] = (U - rhs_of(idx)) * (1.0 / KC_GAMMA);
+      r[idx] = U; Up = U;
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Full right-hand side du = A(x) u for the arrays in shared memory (used for f(u0) and the initial-step
+// heuristic only; the stepper itself never evaluates the RHS).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rhs_full(const DevCosmo& c, const Lane& ln, const Bg& b, const double* u, double* du) {
+  Metric m;
+  const int iS = ln.iS;
+  m.Phi = u[iS]; m.delta = u[iS + 1]; m.v = u[iS + 2]; m.delta_b = u[iS + 3]; m.v_b = u[iS + 4];
+  double c0 = 0, c2 = 0;
+  if (ln.kind != CH_IDLE) { c0 = u[ln.base]; c2 = u[ln.base + 2 * ln.stride]; }
+  metric_from_chains(ln, b, c0, c2, m, c);
+  const double T1 = shfl_d(ln.kind == CH_T ? u[ln.base + ln.stride] : 0.0, ln.nq);
+  auto get = [&](int l) { return u[ln.base + l * ln.stride]; };
+  for (int l = 0; l < ln.len; l++) du[ln.base + l * ln.stride] = rhs_row(ln, b, m, l, get);
+  if (ln.lane == 0) {   // :197-200
+    du[iS] = m.dPhi;
+    du[iS + 1] = b.kappa * m.v - 3.0 * m.dPhi;
+    du[iS + 2] = -m.v - b.kappa * m.Psi;
+    du[iS + 3] = b.kappa * m.v_b - 3.0 * m.dPhi;
+    du[iS + 4] = -m.v_b - b.kappa * (m.Psi + b.csb2 * m.delta_b) + b.taup * b.R * (3.0 * T1 + m.v_b);
+  }
+  __syncwarp();
+}
+
+// initial_conditions (perturbations.jl:274-338) written into u[] (shared)
+__device__ __forceinline__ void initial_conditions(const DevCosmo& c, const Lane& ln, const Bg& b, double* u) {
+  const double k = ln.k, Hx = b.H, eta = b.eta, taup = b.taup;
+  const double N_nu = c.s[BOLT_S_N_nu];
+  const double f_nu = 1.0 / (1.0 + 1.0 / (7.0 * (3.0 / 3.0) * N_nu / 8.0 * pow(4.0 / 11.0, 4.0 / 3.0)));
+  const double Phi = (4.0 * f_nu + 10.0) / (4.0 * f_nu + 15.0) * 1.0;
+  const double C = -((15.0 + 4.0 * f_nu) / (20.0 + 8.0 * f_nu)) * Phi;
+  const double T0 = -40.0 * C / (15.0 + 4.0 * f_nu) / 4.0;
+  const double T1 = 10.0 * C / (15.0 + 4.0 * f_nu) * (k * k * eta) / (3.0 * k);
+  const double T2 = -8.0 * k / (15.0 * Hx * taup) * T1;
+  const double N2 = -(k * k * eta * eta) / 15.0 * 1.0 / (1.0 + 2.0 / 5.0 * f_nu) * Phi / 2.0;
+  if (ln.kind == CH_T) {
+    u[ln.base] = T0; u[ln.base + 1] = T1; u[ln.base + 2] = T2;
+    double prev = T2;
+    for (int l = 3; l < ln.len; l++) { prev = -(double)l / (2 * l + 1) * k / (Hx * taup) * prev; u[ln.base + l] = prev; }
+  } else if (ln.kind == CH_P) {
+    u[ln.base] = (5.0 / 4.0) * T2; u[ln.base + 1] = -k / (4.0 * Hx * taup) * T2;
+    double prev = (1.0 / 4.0) * T2; u[ln.base + 2] = prev;
+    for (int l = 3; l < ln.len; l++) { prev = -(double)l / (2 * l + 1) * k / (Hx * taup) * prev; u[ln.base + l] = prev; }
+  } else if (ln.kind == CH_N) {
+    u[ln.base] = T0; u[ln.base + 1] = T1; u[ln.base + 2] = N2;
+    double prev = N2;
+    for (int l = 3; l < ln.len; l++) { prev = k / ((2 * l + 1) * Hx) * prev; u[ln.base + l] = prev; }
+  } else if (ln.kind == CH_M) {
+    const double df0 = ln.df0;
+    u[ln.base] = -T0 * df0;
+    u[ln.base + ln.stride] = -b.eq * T1 * df0;
+    double prev = -N2 * df0; u[ln.base + 2 * ln.stride] = prev;
+    for (int l = 3; l < ln.len; l++) { prev = b.qe * k / ((2 * l + 1) * Hx) * prev; u[ln.base + l * ln.stride] = prev; }
+  }
+  if (ln.lane == 0) {
+    const double delta = 3.0 / 4.0 * (4.0 * T0), v = -3.0 * k * T1;
+    u[ln.iS] = Phi; u[ln.iS + 1] = delta; u[ln.iS + 2] = v; u[ln.iS + 3] = delta; u[ln.iS + 4] = v;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One sample of the source grids at x_grid[ix] from the Hermite dense output of the current step
+// (spectra.jl:13-18: u = perturb(x); hierarchy!(du,u,h,x); source_function(du,u,h,x)).
+// Only chain rows l <= 3 enter the sources, so only u_l, l <= 4 is interpolated (all of u if u_hist).
+// ---------------------------------------------------------------------------------------------------
+struct Hermite { double th, c0, c1, d0, d1; };   // u(th) = c0*u0 + c1*u1 + d0*(dt f0) + d1*(dt f1)
+__device__ __forceinline__ Hermite hermite_weights(double th) {
+  // (1-th) y0 + th y1 + th(th-1)[(1-2th)(y1-y0) + (th-1) dt f0 + th dt f1]   [OrdinaryDiffEq hermite_interpolant]
+  Hermite hm; hm.th = th;
+  const double w = th * (th - 1.0);
+  hm.c0 = (1.0 - th) - w * (1.0 - 2.0 * th);
+  hm.c1 = th + w * (1.0 - 2.0 * th);
+  hm.d0 = w * (th - 1.0);
+  hm.d1 = w * th;
+  return hm;
+}
+
+__device__ __forceinline__ void sample_sources(const DevCosmo& c, const Lane& ln, const SolveParams& p, int ik, int ix, double xs,
+                                               const Hermite& hm, const double* u0, const double* u1, const double* z1, double s1,
+                                               const double* z6, bool& rsa_flag) {
+  auto herm = [&](int idx) { return hm.c0 * u0[idx] + hm.c1 * u1[idx] + hm.d0 * (s1 * z1[idx]) + hm.d1 * z6[idx]; };
+  if (p.u_hist) {
+    double* out = p.u_hist + ((size_t)ik * c.n_x + ix) * ln.n;
+    for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; out[idx] = herm(idx); }
+    if (ln.lane < 5) out[ln.iS + ln.lane] = herm(ln.iS + ln.lane);
+  }
+  if (!p.S_T && !p.S_P) return;
+  Bg b; eval_bg(c, ln, xs, b);
+  // remaining tables of source_function (:347-349): lanes evaluate one each
+  const int which[5] = {BOLT_T_Hpp, BOLT_T_tau, BOLT_T_g, BOLT_T_gp, BOLT_T_gpp};
+  double tv = 0.0;
+  if (ln.lane < 5) tv = spline_eval(c.tab[which[ln.lane]], c.n_x, c.x0, c.dx, xs);
+  const double Hpp = shfl_d(tv, 0), tau = shfl_d(tv, 1), g = shfl_d(tv, 2), gp = shfl_d(tv, 3), gpp = shfl_d(tv, 4);
+  double uL[5] = {0, 0, 0, 0, 0};
+  if (ln.kind != CH_IDLE) {
+#pragma unroll
+    for (int l = 0; l < 5; l++) if (l < ln.len) uL[l] = herm(ln.base + l * ln.stride);
+  }
+  Metric m;
+  m.Phi = herm(ln.iS); m.delta = herm(ln.iS + 1); m.v = herm(ln.iS + 2); m.delta_b = herm(ln.iS + 3); m.v_b = herm(ln.iS + 4);
+  metric_from_chains(ln, b, uL[0], uL[2], m, c);
+  auto get = [&](int l) { double v = uL[0]; v = (l == 1) ? uL[1] : v; v = (l == 2) ? uL[2] : v; v = (l == 3) ? uL[3] : v; v = (l == 4) ? uL[4] : v; return v; };
+  double d[4] = {0, 0, 0, 0};
+  if (ln.kind != CH_IDLE) {
+#pragma unroll
+    for (int l = 0; l < 4; l++) d[l] = rhs_row(ln, b, m, l, get);
+  }
+  const double T1 = shfl_d(uL[1], ln.nq);
+  const double dvb = -m.v_b - b.kappa * (m.Psi + b.csb2 * m.delta_b) + b.taup * b.R * (3.0 * T1 + m.v_b);   // :200
+  // RSA switch (:216-232): overwrite Theta_0..2, N_0..2 in the sampled state and zero the radiation derivatives
+  const bool rsa_on = (ln.k * b.eta > 240.0) && (-b.taup * b.H / b.eta > 100.0);
+  if (rsa_on) {
+    rsa_flag = true;
+    if (ln.kind == CH_T) {
+      uL[0] = m.Phi - b.H / ln.k * b.taup * m.v_b;
+      uL[1] = b.H / ln.k * (-2.0 * m.dPhi + b.taup * (m.Phi - b.csb2 * m.delta_b) + b.H / ln.k * (b.taupp - b.taup) * m.v_b);
+      uL[2] = 0.0;
+    } else if (ln.kind == CH_N) {
+      uL[0] = m.Phi; uL[1] = -2.0 * b.H / ln.k * m.dPhi; uL[2] = 0.0;
+    }
+    if (ln.kind == CH_T || ln.kind == CH_P || ln.kind == CH_N) { d[0] = d[1] = d[2] = d[3] = 0.0; }
+  }
+  // sigma_M and its derivative (:361-362)
+  const double wS = (ln.kind == CH_M) ? b.wPsi * 4.0 * c.s[BOLT_S_rho_crit] : 0.0;   // wq q^2/eps
+  const double sigM = warp_sum(wS * uL[2]);
+  const double sigMp = warp_sum(wS * d[2]);
+  const int lT = ln.nq, lP = ln.nq + 1, lN = ln.nq + 2;
+  const double Th0 = shfl_d(uL[0], lT), Th1 = shfl_d(uL[1], lT), Th2 = shfl_d(uL[2], lT), Th3 = shfl_d(uL[3], lT);
+  const double dTh1 = shfl_d(d[1], lT), dTh2 = shfl_d(d[2], lT), dTh3 = shfl_d(d[3], lT);
+  const double P0 = shfl_d(uL[0], lP), P1 = shfl_d(uL[1], lP), P2 = shfl_d(uL[2], lP), P3 = shfl_d(uL[3], lP);
+  const double dP0 = shfl_d(d[0], lP), dP1 = shfl_d(d[1], lP), dP2 = shfl_d(d[2], lP), dP3 = shfl_d(d[3], lP);
+  const double N2 = shfl_d(uL[2], lN), dN2 = shfl_d(d[2], lN);
+  const double Om_r = c.s[BOLT_S_Omega_r], rho_crit = c.s[BOLT_S_rho_crit];
+  const double k = ln.k, Hx = b.H, Hp = b.Hp;
+  const double Psi = -m.Phi - b.cPsi * (Om_r * Th2 + c.Omega_nu * N2 + sigM / rho_crit / 4.0);                 // :363-365
+  const double dPsi = -m.dPhi - b.cPsi * (Om_r * (dTh2 - 2.0 * Th2) + c.Omega_nu * (dN2 - 2.0 * N2)
+                                          + (sigMp - 2.0 * sigM) / rho_crit / 4.0);                           // :368-370
+  const double Pi = Th2 + P2 + P0, dPi = dTh2 + dP2 + dP0;                                                     // :372-373
+  const double term1 = g * (Th0 + Psi + Pi / 4.0) + exp(-tau) * (dPsi - m.dPhi);                                // :375
+  const double term2 = (-1.0 / k) * (Hp * g * m.v_b + Hx * gp * m.v_b + Hx * g * dvb);                          // :376
+  const double ddPi = 2.0 * k / (5.0 * Hx) * (-Hp / Hx * Th1 + dTh1) + (3.0 / 10.0) * (b.taupp * Pi + b.taup * dPi)
+                      - 3.0 * k / (5.0 * Hx) * (-Hp / Hx * (Th3 + P1 + P3) + (dTh3 + dP1 + dP3));               // :377-378
+  const double term3 = (3.0 / (4.0 * k * k)) * ((Hp * Hp + Hx * Hpp) * g * Pi + 3.0 * Hx * Hp * (gp * Pi + g * dPi)
+                                                + Hx * Hx * (gpp * Pi + 2.0 * gp * dPi + g * ddPi));            // :379-381
+  const double y = k * (c.eta_end - b.eta);                                                                    // :401
+  if (ln.lane == 0) {
+    if (p.S_T) p.S_T[(size_t)ik * c.n_x + ix] = term1 + term2 + term3;
+    if (p.S_P) p.S_P[(size_t)ik * c.n_x + ix] = (3.0 / (4.0 * y * y)) * g * Pi;                                 // :403
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The kernel: persistent warps pull k-modes from a queue.
+// Shared memory per warp: 9 arrays of n doubles: u, z1..z6, work r, inverse pivots ib.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) hierarchy_kernel(SolveParams p) {
+  extern __shared__ double sm[];
+  const DevCosmo& c = *p.cos;
+  const int n = p.n;
+  Lane ln;
+  ln.lane = threadIdx.x; ln.nq = c.nq; ln.L = p.L; ln.n = n;
+  ln.iS = 2 * (p.L + 1) + (p.Lnu + 1) + (p.Lm + 1) * c.nq;
+  ln.maxlen = max(p.L, max(p.Lnu, p.Lm)) + 1;
+  ln.q = 0; ln.df0 = 0; ln.wq = 0;
+  if (ln.lane < c.nq) { ln.kind = CH_M; ln.base = 2 * (p.L + 1) + (p.Lnu + 1) + ln.lane; ln.stride = c.nq; ln.len = p.Lm + 1;
+                        ln.q = c.q[ln.lane]; ln.df0 = c.df0[ln.lane]; ln.wq = c.wq[ln.lane]; }
+  else if (ln.lane == c.nq) { ln.kind = CH_T; ln.base = 0; ln.stride = 1; ln.len = p.L + 1; }
+  else if (ln.lane == c.nq + 1) { ln.kind = CH_P; ln.base = p.L + 1; ln.stride = 1; ln.len = p.L + 1; }
+  else if (ln.lane == c.nq + 2) { ln.kind = CH_N; ln.base = 2 * (p.L + 1); ln.stride = 1; ln.len = p.Lnu + 1; }
+  else { ln.kind = CH_IDLE; ln.base = 0; ln.stride = 0; ln.len = 0; }
+
+  const double x_begin = c.x0, x_end = 0.0;
+  const bool fixed = (p.mode == BOLT_MODE_FIXED);
+  const double reltol = p.reltol, abstol = p.abstol;
+
+  while (true) {
+    int w = 0;
+    if (ln.lane == 0) w = atomicAdd(p.counter, 1);
+    w = __shfl_sync(FULL, w, 0);
+    if (w >= p.nk) break;
+    const int ik = p.order[w];
+    ln.k = p.k[ik];
+
+    // Array slots.  u/u_{n+1} and z1/z6 swap roles on every accepted step (no copies): physical slot 0/2
+    // hold u and u_{n+1} (alias of the z2 slot, which is free once the error estimate is formed), slots
+    // 1/6 hold z1 and z6.  z3..z5 are fixed.
+    bool flipU = false, flipZ = false;
+    double* const Z2 = sm + (size_t)3 * n;
+    double* const Z3 = sm + (size_t)4 * n;
+    double* const Z4 = sm + (size_t)5 * n;
+    double* r = sm + (size_t)7 * n;
+    double* ib = sm + (size_t)8 * n;
+#define SLOT_U  (sm + (flipU ? (size_t)2 * n : (size_t)0))
+#define SLOT_Z1 (sm + (flipU ? (size_t)0 : (size_t)2 * n))
+#define SLOT_Z0 (sm + (flipZ ? (size_t)6 * n : (size_t)n))
+#define SLOT_Z5 (sm + (flipZ ? (size_t)n : (size_t)6 * n))
+    double* U = SLOT_U; double* Z0 = SLOT_Z0; double* Z1 = SLOT_Z1; double* Z5 = SLOT_Z5;
+
+    Bg b;
+    eval_bg(c, ln, x_begin, b);
+    initial_conditions(c, ln, b, U);
+    rhs_full(c, ln, b, U, Z5);          // f(u0) in Z[5] (plays the role of z6/dt of a previous step)
+    bool rsa_flag = (ln.k * b.eta > 240.0) && (-b.taup * b.H / b.eta > 100.0);
+
+    int ix = 0;
+    int status = BOLT_K_OK;
+    long long nsteps = 0, nreject = 0;
+    // first sample: sol(x0) = u0  (theta = 0)
+    if (ix >= p.ix_first) { Hermite h0 = hermite_weights(0.0); sample_sources(c, ln, p, ik, 0, x_begin, h0, U, U, Z5, 0.0, Z5, rsa_flag); }
+    ix = 1;
+
+    double x = x_begin, dt;
+    auto sumsq_scaled = [&](const double* num, const double* a0, const double* a1) {
+      double s = 0.0;
+      for (int l = 0; l < ln.len; l++) {
+        const int idx = ln.base + l * ln.stride;
+        const double sc = abstol + reltol * fmax(fabs(a0[idx]), fabs(a1[idx]));
+        const double q = num[idx] / sc; s += q * q;
+      }
+      if (ln.lane < 5) {
+        const int idx = ln.iS + ln.lane;
+        const double sc = abstol + reltol * fmax(fabs(a0[idx]), fabs(a1[idx]));
+        const double q = num[idx] / sc; s += q * q;
+      }
+      return warp_sum(s);
+    };
+    if (fixed) {
+      dt = p.fixed_dt;
+    } else {
+      // initial step, Hairer-Wanner as in OrdinaryDiffEq's ode_determine_initdt (same as the oracle)
+      const double d0 = sqrt(sumsq_scaled(U, U, U) / n), d1 = sqrt(sumsq_scaled(Z5, U, U) / n);
+      double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+      dt0 = fmin(dt0, x_end - x_begin);
+      for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; r[idx] = U[idx] + dt0 * Z5[idx]; }
+      if (ln.lane < 5) { const int idx = ln.iS + ln.lane; r[idx] = U[idx] + dt0 * Z5[idx]; }
+      __syncwarp();
+      Bg b1; eval_bg(c, ln, x_begin + dt0, b1);
+      rhs_full(c, ln, b1, r, Z0);
+      for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; Z0[idx] -= Z5[idx]; }
+      if (ln.lane < 5) { const int idx = ln.iS + ln.lane; Z0[idx] -= Z5[idx]; }
+      __syncwarp();
+      const double d2 = sqrt(sumsq_scaled(Z0, U, U) / n) / dt0;
+      const double dm = fmax(d1, d2);
+      const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) / 5.0);
+      dt = fmin(100.0 * dt0, dt1);
+    }
+    // Z[0] <- f(u0): true z1 = s1 * Z[0] with s1 = dt
+    flipZ = !flipZ; Z0 = SLOT_Z0; Z5 = SLOT_Z5;
+    double s1 = dt;
+
+    const double beta1 = 7.0 / 40.0, beta2 = 2.0 / 20.0, safety = 0.9, qmin = 0.2, qmax = 10.0;
+    double qold = 1e-4;
+    const long long fixed_total = fixed ? llround((x_end - x_begin) / p.fixed_dt) : 0;
+    long long fixed_left = fixed_total;
+    const long long max_steps = p.max_steps > 0 ? p.max_steps : 1000000;
+
+    while (true) {
+      bool clamped = false;
+      if (fixed) { if (fixed_left == 0) break; }
+      else {
+        if (x >= x_end) break;
+        if (x + dt >= x_end) { const double dtn = x_end - x; s1 *= dtn / dt; dt = dtn; clamped = true; }
+      }
+      if (nsteps + nreject >= max_steps) { status = BOLT_K_MAXSTEPS; break; }
+
+      Factor f;
+      Bg bs;
+      for (int s = 1; s < 6; s++) {
+        const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
+        const double* z0 = Z0; const double* z1p = Z1; const double* z2p = Z2; const double* z3p = Z3; const double* z4p = Z4;
+        auto rhs_of = [&](int idx) {
+          double v = U[idx] + a0 * z0[idx];
+          if (s > 1) v += a1 * z1p[idx];
+          if (s > 2) v += a2 * z2p[idx];
+          if (s > 3) v += a3 * z3p[idx];
+          if (s > 4) v += a4 * z4p[idx];
+          return v;
+        };
+        for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; r[idx] = rhs_of(idx); }
+        if (ln.lane < 5) { const int idx = ln.iS + ln.lane; r[idx] = rhs_of(idx); }
+        __syncwarp();
+        eval_bg(c, ln, x + KC_C[s] * dt, bs);
+        rsa_flag |= (ln.k * bs.eta > 240.0) && (-bs.taup * bs.H / bs.eta > 100.0);
+        factor(c, ln, bs, KC_GAMMA * dt, ib, f);
+        double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
+        solve(c, ln, bs, f, ib, r, zout, rhs_of);
+      }
+      // error estimate err = sum (b - bhat)_j z_j, and u_{n+1} = u_n + sum b_j z_j (= U_6 up to rounding).
+      // u_{n+1} goes to the Z[1] slot, which is free once err is formed.
+      {
+        const double e0 = KC_E[0] * s1, b0 = KC_A[5][0] * s1;
+        auto pass = [&](int idx) {
+          const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
+          r[idx] = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
+          Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
+        };
+        for (int l = 0; l < ln.len; l++) pass(ln.base + l * ln.stride);
+        if (ln.lane < 5) pass(ln.iS + ln.lane);
+        __syncwarp();
+      }
+      bool accept = true; double EEst = 0.0, q11 = 0.0;
+      if (!fixed) {
+        auto none = [&](int) { return 0.0; };
+        solve(c, ln, bs, f, ib, r, (double*)nullptr, none);      // smooth_est: W^{-1} err with the last stage's W
+        EEst = sqrt(sumsq_scaled(r, U, Z1) / n);
+        if (!isfinite(EEst)) { status = BOLT_K_NONFINITE; break; }
+        q11 = pow(EEst, beta1);
+        accept = EEst <= 1.0;
+      }
+      if (accept) {
+        const bool last = fixed ? (fixed_left == 1) : clamped;
+        const double xn1 = last ? x_end : (fixed ? (x_begin + (double)(fixed_total - fixed_left + 1) * p.fixed_dt) : (x + dt));
+        while (ix < c.n_x) {
+          const double xs = c.x0 + c.dx * ix;
+          if (!last && xs > xn1 + 1e-12) break;
+          if (ix >= p.ix_first) {
+            double th = (xs - x) / dt; if (th > 1.0) th = 1.0;
+            Hermite hm = hermite_weights(th);
+            sample_sources(c, ln, p, ik, ix, xs, hm, U, Z1, Z0, s1, Z5, rsa_flag);
+          }
+          ix++;
+        }
+        x = xn1; nsteps++;
+        // rotate: u <- u_{n+1}; z1 <- z6 (scaled by dt_new/dt through s1)
+        flipU = !flipU; flipZ = !flipZ; U = SLOT_U; Z1 = SLOT_Z1; Z0 = SLOT_Z0; Z5 = SLOT_Z5;
+        if (fixed) { fixed_left--; s1 = 1.0; }
+        else {
+          double q = q11 / pow(qold, beta2);
+          q = fmax(1.0 / qmax, fmin(1.0 / qmin, q / safety));
+          if (q <= 1.2 && q >= 1.0) q = 1.0;
+          qold = fmax(EEst, 1e-4);
+          const double dtn = dt / q;
+          s1 = dtn / dt; dt = dtn;
+        }
+      } else {
+        nreject++;
+        const double dtn = dt / fmin(1.0 / qmin, q11 / safety);
+        s1 *= dtn / dt; dt = dtn;
+        if (!(dt > 1e-14)) { status = BOLT_K_DT_UNDERFLOW; break; }
+      }
+    }
+    if (rsa_flag && status == BOLT_K_OK) status = BOLT_K_RSA_TRIGGERED;
+    if (p.u_final) {
+      double* out = p.u_final + (size_t)ik * n;
+      for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; out[idx] = U[idx]; }
+      if (ln.lane < 5) out[ln.iS + ln.lane] = U[ln.iS + ln.lane];
+    }
+    if (ln.lane == 0) {
+      if (p.status) p.status[ik] = status;
+      if (p.nsteps) p.nsteps[ik] = nsteps;
+      if (p.nreject) p.nreject[ik] = nreject;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace bolt
