@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on B200 (contract: one JSON line on stdout from rank 0).
+
+Workload (config.workload = "C3-value"): BASELINE.json configs[2] without gradients -- per cosmology 2000
+quadratic k-modes (0.1 H0 .. 1000 H0), l_gamma = 8 (state n = 197, massive neutrinos always in the state),
+adaptive KenCarp4 at reltol 1e-11 / abstol 1e-6 (the reference's source_grid defaults), then TT/TE/EE C_l
+for l = 2..2500 on the 5000-point dense k grid.  A "step" = that whole pipeline for ONE synthetic cosmology
+per GPU.  Multi-GPU: cosmologies shard over ranks with no data-path collective (weak scaling).
+
+  value  = k-mode hierarchy solves/s of the whole job (all ranks), spline tables already resident in HBM
+  e2e    = same metric through the reference-facing API with HOST buffers: every step uploads the cosmology's
+           tables (H2D), runs bolt_spectra and reads C_l back (D2H)
+  --impl reference : the oracle port (C++/OpenMP, all host cores) on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NK, ELL_MIN, ELL_MAX, LG, RELTOL, ABSTOL = 2000, 2, 2500, 8, 1e-11, 1e-6
+SEED = 20261017
+
+
+def synthetic_params(i):
+    """Synthetic ΛCDM(+massive ν) parameter draws (SURVEY 8d ranges), deterministic in (SEED, i)."""
+    import bolt_b200 as B
+    from bolt_b200.host import constants as K
+    rng = np.random.default_rng([SEED, i])
+    u = rng.random(6)
+    return B.CosmoParams(h=0.60 + 0.20 * u[0], Ω_b=0.040 + 0.015 * u[1], Ω_c=0.20 + 0.10 * u[2], n=0.92 + 0.08 * u[3],
+                         A=1e-10 * np.exp(2.9 + 0.3 * u[4]), Σm_ν=0.3 * u[5] * K.mass_natural)
+
+
+def make_host_cosmo(i):
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    par = synthetic_params(i)
+    bg = B.Background(par)
+    ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+    hc = abi.HostCosmo.from_host(par, bg, ih)
+    k = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, NK)
+    ix_start = int(np.argmax(bg.x_grid > -8))
+    return dict(par=par, bg=bg, hc=hc, k=k, ix_start=ix_start, kd=(0.01 * bg.H0, 1000 * bg.H0, 5000))
+
+
+def f_step(n):
+    """Algorithmic FP64 flop of one (accepted or rejected) KenCarp4 step of the structured solver:
+    5 stages x (assemble 6n + factor 6n + solve 8n + stage increment 8n + border 600) + error pass 22n +
+    smoothing solve 14n + 300 + norm 6n."""
+    return 182.0 * n + 3300.0
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for j, nm in enumerate(names) if any(len(r) >= 6 and r[2 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_sample(hcosmo, kstride=50, nell=25):
+    """The oracle port (all host cores) on a bounded sample of the step; returns extrapolated solves/s of a full step."""
+    from bolt_b200 import abi
+    from oracle.oracle import OracleCosmo, lib
+    oc = OracleCosmo(hcosmo["hc"])
+    cores = lib().oracle_num_threads()
+    o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL, ix_first=hcosmo["ix_start"])
+    ks = np.ascontiguousarray(hcosmo["k"][kstride // 2::kstride])
+    t0 = time.perf_counter(); out = oc.solve(ks, o, want=("S_T", "S_P")); t_solve = time.perf_counter() - t0
+    ells = np.unique(np.linspace(ELL_MIN, ELL_MAX, nell).astype(np.int32))
+    kmin, kmax, nkd = hcosmo["kd"]
+    t0 = time.perf_counter(); oc.project(out["S_T"], out["S_P"], ks, ells, kmin, kmax, nkd, hcosmo["ix_start"]); t_proj = time.perf_counter() - t0
+    t_full = t_solve * (NK / len(ks)) + t_proj * ((ELL_MAX - ELL_MIN + 1) / len(ells))
+    return dict(value=NK / t_full, unit="k-mode solves/s", cores=cores, kind="port",
+                sample=f"every {kstride}th of the {NK} k-modes ({len(ks)} adaptive solves, {t_solve:.1f}s) + {len(ells)} of "
+                       f"{ELL_MAX - ELL_MIN + 1} multipoles ({t_proj:.1f}s), OpenMP over k and l, extrapolated linearly to the full step; "
+                       "C++ restatement with zero-skipping dense LU (faster than the reference's dense LU), not Julia"), t_solve + t_proj
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "C3-value: per cosmology 2000 quadratic k-modes (n=197, l_gamma=8, l_nu=8, l_mnu=10, nq=15), adaptive KenCarp4 "
+                          "reltol 1e-11/abstol 1e-6, TT+TE+EE C_l for l=2..2500 on the 5000-point dense k grid; gradients not included",
+              "cosmologies_per_step_per_gpu": 1, "parallelism": f"cosmology-sharded x{args.gpus} (no data-path collective)",
+              "l2": "no explicit flush: each step re-creates >330 MB of intermediates (Bessel tables 200 MB, dense source grids 64 MB, "
+                    "source grids 64 MB) > 126 MB L2, and alternates between two cosmologies"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        hcos = make_host_cosmo(0)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            cb, _ = cpu_sample(hcos)
+            if i >= args.warmup:
+                vals.append(cb["value"])
+            if i == 0 and args.warmup > 1:      # the CPU path has no warm-up effects worth minutes of host time
+                args.warmup = 1
+        v = float(np.mean(vals))
+        cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": "kmode_hierarchy_solves_per_s", "value": v, "unit": "k-mode solves/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * NK / v,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "k-mode solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bolt_b200 import abi, capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = capi.Context(local_rank)
+    # two synthetic cosmologies per rank, alternated between steps
+    hcos = [make_host_cosmo(2 * rank + j) for j in range(2)]
+    dcs = [capi.DeviceCosmo(ctx, h["hc"]) for h in hcos]
+    ells = np.arange(ELL_MIN, ELL_MAX + 1, dtype=np.int32)
+    n = abi.state_dim(LG, 8, 10, 15)
+
+    def step(i):
+        h, dc = hcos[i % 2], dcs[i % 2]
+        o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL)
+        kmin, kmax, nkd = h["kd"]
+        tt, te, ee, st, ns = dc.spectra(h["k"], o, ells, kmin, kmax, nkd, h["ix_start"])
+        return tt, te, ee, st, ns, ctx.timing()
+
+    def step_e2e(i):
+        h = hcos[i % 2]
+        dc = capi.DeviceCosmo(ctx, h["hc"])            # H2D: tables + scalars + quadrature
+        o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL)
+        kmin, kmax, nkd = h["kd"]
+        out = dc.spectra(h["k"], o, ells, kmin, kmax, nkd, h["ix_start"])   # H2D k, ells ; D2H C_l, status, nsteps
+        dc.close()
+        return out
+
+    for i in range(args.warmup):
+        step(i)
+    fp64_peak = ctx.fp64_peak_tflops()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, k1_ms, k2_ms, bes_ms, flops, launches, nstep_tot = 0.0, 0.0, 0.0, 0.0, 0.0, 0, 0
+    bad = 0
+    for i in range(args.steps):
+        tt, te, ee, st, ns, tm = step(args.warmup + i)
+        dev_ms += tm["total_ms"]; k1_ms += tm["hierarchy_ms"]; k2_ms += tm["project_ms"]; bes_ms += tm["bessel_ms"]
+        launches += tm["hierarchy_launches"] + tm["bessel_launches"] + tm["project_launches"]
+        nstep_tot += int(ns.sum()); bad += int((st != 0).sum())
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # e2e arm
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+
+    times = torch.tensor([wall, wall_e2e, dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    wall_max, e2e_max, dev_max = [float(v) for v in times.tolist()]
+    if rank == 0:
+        total_solves = NK * args.steps * world
+        value = total_solves / wall_max
+        # rejected steps cost the same as accepted ones; nreject is not returned by bolt_spectra: use the oracle-verified
+        # ratio from the accepted count only (lower bound on work)
+        fl = nstep_tot * f_step(n)
+        roof = {"kernel": "hierarchy_kernel (K1, dominant)", "bound": "fp64", "achieved": fl / (k1_ms * 1e-3) / 1e12, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": fl / (k1_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None, "traffic": None,
+                "peak_source": "DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
+                "note": "algorithmic flop = accepted steps x (182 n + 3300), n = 197 (DESIGN.md); latency-bound by the longest k-mode"}
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            hbm_peak = 6650.0
+        nell = len(ells)
+        k2_bytes = (2 * 799 * 4999 * 8) + nell * 5003 * 8      # one read of the dense source grids + the spline tables
+        k2_terms = 2.0 * nell * 4999 * 799
+        roof_k2 = {"kernel": "project_kernel (K2)", "bound": "hbm", "achieved": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                   "unit": "GB/s", "frac": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                   "fp64_tflops": 25.0 * k2_terms / 2 * args.steps / (k2_ms * 1e-3) / 1e12,
+                   "note": "K2 is FP64/shared-memory-gather bound, not HBM bound (SURVEY 8d): both figures reported"}
+        line = {"metric": "kmode_hierarchy_solves_per_s", "value": value, "unit": "k-mode solves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "spectra_per_s": args.steps * world / wall_max, "device_ms_per_step": dev_max / args.steps,
+                "kernel_ms_per_step": {"hierarchy": k1_ms / args.steps, "bessel_tables": bes_ms / args.steps, "projection": k2_ms / args.steps},
+                "ode_steps_per_solve": nstep_tot / (NK * args.steps), "failed_modes": bad,
+                "roofline": roof, "roofline_k2": roof_k2, "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": total_solves / e2e_max, "unit": "k-mode solves/s",
+                        "h2d_bytes_per_step": int(hcos[0]["hc"].tables.nbytes + hcos[0]["hc"].scalars.nbytes + 2 * 15 * 8 + NK * 8 + nell * 4 + 2 * NK * 4),
+                        "d2h_bytes_per_step": int(3 * nell * 8 + NK * 4 + NK * 8)}}
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = cpu_sample(hcos[0])
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

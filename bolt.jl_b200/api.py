@@ -1,0 +1,288 @@
+"""Host-side mirror of the reference's exported function set for the hot path (src/Bolt.jl:8-9):
+Hierarchy / boltsolve / boltsolve_rsa (src/perturbations.jl:7-33, 86-111), source_grid / source_grid_P,
+quadratic_k / log10_k, cltt / clte / clee, plin (src/spectra.jl).  Same names, argument order, defaults
+and return shapes as the Julia functions; the arithmetic runs in libbolt_cuda.so (no CPU fallback).
+This file is the Python twin of julia/BoltCUDA.jl (the Julia shim cannot be executed in this image).
+"""
+import threading
+import numpy as np
+
+from . import abi, capi
+from .host.background import CosmoParams, Background
+from .host.recfast import RECFAST, IonizationHistory
+
+
+class BasicNewtonian:
+    """src/perturbations.jl:4"""
+
+
+_tls = threading.local()
+
+
+def default_context(device=0):
+    """One bolt_ctx per host thread (the reference calls plin/cltt from many threads)."""
+    ctxs = getattr(_tls, "ctxs", None)
+    if ctxs is None:
+        ctxs = _tls.ctxs = {}
+    if device not in ctxs:
+        ctxs[device] = capi.Context(device)
+    return ctxs[device]
+
+
+def device_cosmo(par, bg, ih, ctx=None):
+    """Upload (once per (bg, ih) pair and context) what Background and IonizationHistory computed on the host."""
+    ctx = ctx or default_context()
+    cache = ih.__dict__.setdefault("_bolt_dev", {})
+    key = (id(ctx), id(bg))
+    if key not in cache:
+        cache[key] = capi.DeviceCosmo(ctx, abi.HostCosmo.from_host(par, bg, ih))
+    return cache[key]
+
+
+class Hierarchy:
+    """src/perturbations.jl:7-21"""
+
+    def __init__(self, integrator, par, bg, ih, k, ℓᵧ=8, ℓ_ν=8, ℓ_mν=10, nq=15):
+        if nq != bg.nq:
+            raise ValueError("nq must match the background's quadrature (bg.quad_pts)")
+        self.integrator, self.par, self.bg, self.ih, self.k = integrator, par, bg, ih, float(k)
+        self.ℓᵧ, self.ℓ_ν, self.ℓ_mν, self.nq = ℓᵧ, ℓ_ν, ℓ_mν, nq
+
+    @property
+    def n(self):
+        return abi.state_dim(self.ℓᵧ, self.ℓ_ν, self.ℓ_mν, self.nq)
+
+
+class Solution:
+    """What boltsolve returns: callable like the reference's ODESolution, `sol(x) -> Vector(n)`.
+    The solution is held on bg.x_grid (the device's Hermite dense output sampled at every grid point);
+    between grid points it is interpolated linearly (documented deviation: the reference interpolates
+    between its own adaptive steps)."""
+
+    def __init__(self, x_grid, u, status, nsteps):
+        self.t, self.u, self.retcode, self.nsteps = x_grid, u, int(status), int(nsteps)
+
+    def __call__(self, x):
+        t = (x - self.t[0]) / (self.t[1] - self.t[0])
+        i = int(np.clip(np.floor(t), 0, len(self.t) - 2))
+        w = t - i
+        return (1 - w) * self.u[i] + w * self.u[i + 1]
+
+
+def _opts(h_or_trunc, reltol, abstol, **kw):
+    ℓᵧ, ℓ_ν, ℓ_mν = h_or_trunc
+    return abi.make_opts(ℓᵧ, ℓ_ν, ℓ_mν, reltol=reltol, abstol=abstol, **kw)
+
+
+def boltsolve(hierarchy, ode_alg=None, reltol=1e-6, abstol=1e-6, ctx=None):
+    """src/perturbations.jl:25-33.  `ode_alg` is accepted for signature compatibility; the device
+    runs KenCarp4's ESDIRK tableau."""
+    h = hierarchy
+    dc = device_cosmo(h.par, h.bg, h.ih, ctx)
+    out = dc.solve(np.array([h.k]), _opts((h.ℓᵧ, h.ℓ_ν, h.ℓ_mν), reltol, abstol), want=("u_hist",))
+    return Solution(h.bg.x_grid, out["u_hist"][0], out["status"][0], out["nsteps"][0])
+
+
+def rsa_perts(u, hierarchy, x):
+    """rsa_perts! (src/perturbations.jl:35-84): overwrite Θ₀..₂, 𝒩₀..₂ with the RSA expressions, zero the rest."""
+    h = hierarchy
+    k, ℓᵧ, ℓ_ν, nq, par, bg, ih = h.k, h.ℓᵧ, h.ℓ_ν, h.nq, h.par, h.bg, h.ih
+    H02 = bg.H0 ** 2
+    Hx, ηx, τp, τpp = bg.H(x), bg.η(x), ih.τp(x), ih.τpp(x)
+    a = np.exp(x)
+    Ω_ν = 7 * (2 / 3) * par.N_ν / 8 * (4 / 11) ** (4 / 3) * par.Ω_r
+    csb2 = ih.csb2(x)
+    iN = 2 * (ℓᵧ + 1); iM = iN + ℓ_ν + 1; iS = iM + (h.ℓ_mν + 1) * nq
+    Φ, δ, v, δ_b, v_b = u[iS:iS + 5]
+    from .host.background import q_grid, f0, dxdq
+    q, lqmi, lqma = q_grid(par, bg.quad_pts)
+    eps = np.sqrt(q ** 2 + (a * par.Σm_ν) ** 2)
+    w = f0(q, par) / dxdq(q, lqmi, lqma) * bg.quad_wts
+    ρM = 4 * np.pi * np.sum(q ** 2 * eps * w * u[iM:iM + nq])
+    σM = 4 * np.pi * np.sum(q ** 2 * (q ** 2 / eps) * w * u[iM + 2 * nq:iM + 3 * nq])
+    Ψ = -Φ - 12 * H02 / k ** 2 / a ** 2 * (par.Ω_r * u[2] + Ω_ν * u[iN + 2] + σM / bg.ρ_crit / 4)
+    Φp = Ψ - k ** 2 / (3 * Hx ** 2) * Φ + H02 / (2 * Hx ** 2) * (
+        par.Ω_c / a * δ + par.Ω_b / a * δ_b + 4 * par.Ω_r / a ** 2 * u[0] + 4 * Ω_ν / a ** 2 * u[iN] + ρM / a ** 2 / bg.ρ_crit)
+    u[0] = Φ - Hx / k * τp * v_b
+    u[1] = Hx / k * (-2 * Φp + τp * (Φ - csb2 * δ_b) + Hx / k * (τpp - τp) * v_b)
+    u[2] = 0
+    u[iN] = Φ; u[iN + 1] = -2 * Hx / k * Φp; u[iN + 2] = 0
+    # the reference's zeroing loop uses 1-based u[ℓ] for ℓ in 3:ℓᵧ (perturbations.jl:78-82), reproduced as written
+    for ℓ in range(3, ℓᵧ + 1):
+        u[ℓ - 1] = 0
+        u[(ℓᵧ + 1) + ℓ - 1] = 0
+    for ℓ in range(3, ℓ_ν + 1):
+        u[2 * (ℓᵧ + 1) + ℓ - 1] = 0
+
+
+def boltsolve_rsa(hierarchy, ode_alg=None, reltol=1e-6, abstol=1e-6, ctx=None):
+    """src/perturbations.jl:86-111 -> Matrix(n, n_x) (returned as an array of shape (n, n_x))."""
+    h = hierarchy
+    sol = boltsolve(h, reltol=reltol, abstol=abstol, ctx=ctx)
+    x_grid = h.bg.x_grid
+    results = sol.u.T.copy()
+    kη = h.k * h.bg.η(x_grid)
+    od = -h.ih.τp(x_grid) * h.bg.H(x_grid) / h.bg.η(x_grid)
+    hor = np.nonzero(kη > 240)[0]
+    xrsa_hor = (hor[0] if len(hor) else len(x_grid) - 1)
+    odi = np.nonzero(od > 100)[0]
+    xrsa_od = (odi[0] if len(odi) else len(x_grid) - 1)   # (:99 tests the wrong variable in the reference; same result)
+    switch = x_grid[max(xrsa_hor, xrsa_od)]
+    for i in np.nonzero(x_grid > switch)[0]:
+        col = results[:, i].copy()
+        rsa_perts(col, h, x_grid[i])
+        results[:, i] = col
+    return results
+
+
+class SourceInterpolant:
+    """LinearInterpolation((x_grid, k_grid), grid, extrapolation_bc=Line()) (src/spectra.jl:21)."""
+
+    def __init__(self, x_grid, k_grid, grid, other=None, meta=None):
+        self.x_grid, self.k_grid, self.grid = x_grid, np.asarray(k_grid, dtype=np.float64), grid   # grid[i_x, i_k]
+        self._other, self.meta = other, meta or {}
+
+    def __call__(self, x, k):
+        xg, kg = self.x_grid, self.k_grid
+        tx = (np.asarray(x, dtype=np.float64) - xg[0]) / (xg[1] - xg[0])
+        ix = np.clip(np.floor(tx).astype(int), 0, len(xg) - 2); wx = tx - ix
+        k = np.asarray(k, dtype=np.float64)
+        jk = np.clip(np.searchsorted(kg, k, side="right") - 1, 0, len(kg) - 2)
+        wk = (k - kg[jk]) / (kg[jk + 1] - kg[jk])
+        g = self.grid
+        return ((1 - wx) * (1 - wk) * g[ix, jk] + wx * (1 - wk) * g[ix + 1, jk]
+                + (1 - wx) * wk * g[ix, jk + 1] + wx * wk * g[ix + 1, jk + 1])
+
+
+def _source_grids(par, bg, ih, k_grid, ℓᵧ, reltol, ctx):
+    dc = device_cosmo(par, bg, ih, ctx)
+    k_grid = np.ascontiguousarray(k_grid, dtype=np.float64)
+    out = dc.solve(k_grid, _opts((ℓᵧ, 8, 10), reltol, 1e-6), want=("S_T", "S_P"))
+    meta = dict(status=out["status"], nsteps=out["nsteps"], nreject=out["nreject"])
+    sT = SourceInterpolant(bg.x_grid, k_grid, np.ascontiguousarray(out["S_T"].T), meta=meta)
+    sP = SourceInterpolant(bg.x_grid, k_grid, np.ascontiguousarray(out["S_P"].T), meta=meta)
+    sT._other, sP._other = sP, sT
+    return sT, sP
+
+
+_pair_cache = {}
+
+
+def _pair_key(par, bg, ih, k_grid, ℓᵧ, reltol):
+    return (id(bg), id(ih), np.asarray(k_grid, dtype=np.float64).tobytes(), ℓᵧ, reltol)
+
+
+def source_grid(par, bg, ih, k_grid, integrator, ℓᵧ=8, reltol=1e-11, ctx=None):
+    """src/spectra.jl:6-23.  The device emits the temperature AND polarization source from the same
+    solve, so the sibling grid is cached for a following source_grid_P call with the same arguments."""
+    key = _pair_key(par, bg, ih, k_grid, ℓᵧ, reltol)
+    pair = _pair_cache.pop(key, None)
+    if pair is None:
+        pair = _source_grids(par, bg, ih, k_grid, ℓᵧ, reltol, ctx)
+        _pair_cache.clear(); _pair_cache[key] = pair
+    return pair[0]
+
+
+def source_grid_P(par, bg, ih, k_grid, integrator, ℓᵧ=8, reltol=1e-11, ctx=None):
+    """src/spectra.jl:25-42"""
+    key = _pair_key(par, bg, ih, k_grid, ℓᵧ, reltol)
+    pair = _pair_cache.pop(key, None)
+    if pair is None:
+        pair = _source_grids(par, bg, ih, k_grid, ℓᵧ, reltol, ctx)
+        _pair_cache.clear(); _pair_cache[key] = pair
+    return pair[1]
+
+
+def quadratic_k(kmin, kmax, nk):
+    """src/spectra.jl:60-63"""
+    i = np.arange(1, nk + 1)
+    return kmin + (kmax - kmin) * (i / nk) ** 2
+
+
+def log10_k(kmin, kmax, nk):
+    """src/spectra.jl:65-68"""
+    i = np.arange(1, nk + 1)
+    return 10.0 ** (np.log10(kmin) + (np.log10(kmax / kmin)) * (i - 1) / (nk - 1))
+
+
+def _ix_start(bg):
+    return int(np.argmax(bg.x_grid > -8))       # findfirst(bg.x_grid .> -8), 0-based (src/spectra.jl:86)
+
+
+def _is_quadratic(kgrid):
+    n = len(kgrid)
+    kmin = (kgrid[0] * n * n - kgrid[-1]) / (n * n - 1.0)
+    return np.allclose(quadratic_k(kmin, kgrid[-1], n), kgrid, rtol=1e-13, atol=0), kmin
+
+
+def _project(ells, sT, sP, kd_min, kd_max, n_kd, par, bg, ih, ctx):
+    scalar = np.isscalar(ells)
+    ells = np.atleast_1d(np.asarray(ells, dtype=np.int32))
+    order = np.argsort(ells, kind="stable")
+    ref = sT if sT is not None else sP
+    dc = device_cosmo(par, bg, ih if ih is not None else ref.meta.get("ih"), ctx)
+    tt, te, ee = dc.project(None if sT is None else np.ascontiguousarray(sT.grid.T),
+                            None if sP is None else np.ascontiguousarray(sP.grid.T),
+                            ref.k_grid, ells[order], kd_min, kd_max, n_kd, _ix_start(bg))
+    inv = np.empty_like(order); inv[order] = np.arange(len(order))
+    res = [None if a is None else (a[inv][0] if scalar else a[inv]) for a in (tt, te, ee)]
+    return res
+
+
+def _dense(args, nsrc):
+    """Dispatch the three reference methods: (ℓ, s_itp..., kgrid, par, bg) or (ℓ | ℓ⃗, par, bg, ih, sf...)."""
+    if isinstance(args[1], SourceInterpolant):
+        ell, srcs, kgrid, par, bg = args[0], args[1:1 + nsrc], np.asarray(args[1 + nsrc]), args[2 + nsrc], args[3 + nsrc]
+        ok, kmin = _is_quadratic(kgrid)
+        if not ok:
+            raise NotImplementedError("only quadratic_k dense grids are supported on the device")
+        return ell, srcs, kmin, kgrid[-1], len(kgrid), par, bg, None
+    ell, par, bg, ih, srcs = args[0], args[1], args[2], args[3], args[4:4 + nsrc]
+    return ell, srcs, 0.01 * bg.H0, 1000 * bg.H0, 5000, par, bg, ih     # src/spectra.jl:133,138,143
+
+
+def _ih_of(ih, src):
+    if ih is not None:
+        return ih
+    raise ValueError("the (ℓ, s_itp, kgrid, par, bg) method needs the ionization history that made s_itp; "
+                     "pass ih=... (the Julia method reads nothing from ih either, but the device tables are keyed on it)")
+
+
+def cltt(*args, ih=None, ctx=None):
+    """src/spectra.jl:84-97, 132-135, 147-150"""
+    ell, (sf,), kmin, kmax, n, par, bg, ih2 = _dense(args, 1)
+    return _project(ell, sf, None, kmin, kmax, n, par, bg, _ih_of(ih2 or ih, sf), ctx)[0]
+
+
+def clte(*args, ih=None, ctx=None):
+    """src/spectra.jl:99-114, 137-140, 152-155"""
+    ell, (sf, sfP), kmin, kmax, n, par, bg, ih2 = _dense(args, 2)
+    return _project(ell, sf, sfP, kmin, kmax, n, par, bg, _ih_of(ih2 or ih, sf), ctx)[1]
+
+
+def clee(*args, ih=None, ctx=None):
+    """src/spectra.jl:116-130, 142-145, 157-160"""
+    ell, (sfP,), kmin, kmax, n, par, bg, ih2 = _dense(args, 1)
+    return _project(ell, None, sfP, kmin, kmax, n, par, bg, _ih_of(ih2 or ih, sfP), ctx)[2]
+
+
+def plin(k, par, bg, ih, n_q=15, ℓᵧ=50, ℓ_ν=50, ℓ_mν=20, x=0, reltol=1e-5, ctx=None):
+    """src/spectra.jl:163-198.  Accepts a scalar k (like the reference) or a vector of k (one batched call)."""
+    if x != 0:
+        raise NotImplementedError("plin is evaluated at x = 0 on the device (the reference default)")
+    if n_q != bg.nq:
+        raise ValueError("n_q must match the background's quadrature")
+    dc = device_cosmo(par, bg, ih, ctx)
+    ks = np.atleast_1d(np.asarray(k, dtype=np.float64))
+    pk, status, _ = dc.plin(ks, _opts((ℓᵧ, ℓ_ν, ℓ_mν), reltol, 1e-6))
+    return pk[0] if np.isscalar(k) else pk
+
+
+def spectra(ells, par, bg, ih, k_grid, ℓᵧ=8, reltol=1e-11, ctx=None):
+    """Fused source_grid + source_grid_P + cltt/clte/clee with the source grids kept in HBM
+    (bolt_spectra): the whole-path call the benchmark times."""
+    dc = device_cosmo(par, bg, ih, ctx)
+    ells = np.asarray(ells, dtype=np.int32)
+    tt, te, ee, status, nsteps = dc.spectra(k_grid, _opts((ℓᵧ, 8, 10), reltol, 1e-6), ells, 0.01 * bg.H0, 1000 * bg.H0, 5000,
+                                            _ix_start(bg))
+    return tt, te, ee, dict(status=status, nsteps=nsteps)

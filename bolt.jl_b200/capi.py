@@ -15,7 +15,7 @@ _LIB = None
 
 EXPORTS = ["bolt_abi_version", "bolt_init", "bolt_finalize", "bolt_last_error", "bolt_last_timing",
            "bolt_cosmo_upload", "bolt_cosmo_free", "bolt_state_dim", "bolt_solve", "bolt_project",
-           "bolt_spectra", "bolt_plin"]
+           "bolt_spectra", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak"]
 
 
 class BoltError(RuntimeError):
@@ -44,6 +44,9 @@ def lib():
         L.bolt_spectra.argtypes = [vp, vp, dp, C.c_int, C.POINTER(abi.Opts), ip, C.c_int, C.c_double, C.c_double,
                                    C.c_int, C.c_int, dp, dp, dp, ip, lp]
         L.bolt_plin.argtypes = [vp, vp, dp, C.c_int, C.POINTER(abi.Opts), dp, ip, lp]
+        L.bolt_fp64_peak.argtypes = [vp, dp]
+        L.bolt_solve_device.argtypes = [vp, vp, vp, C.c_int, C.POINTER(abi.Opts), vp, vp, vp, vp, vp, vp]
+        L.bolt_project_device.argtypes = [vp, vp, vp, vp, vp, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, vp]
         _LIB = L
     return _LIB
 
@@ -68,6 +71,11 @@ class Context:
         lib().bolt_last_timing(self._h, abi.ptr(t))
         return dict(hierarchy_ms=t[0], bessel_ms=t[1], project_ms=t[2], total_ms=t[3],
                     hierarchy_launches=int(t[4]), bessel_launches=int(t[5]), project_launches=int(t[6]))
+
+    def fp64_peak_tflops(self):
+        t = np.zeros(1)
+        self.check(lib().bolt_fp64_peak(self._h, abi.ptr(t)))
+        return float(t[0])
 
     def close(self):
         if self._h:
@@ -148,3 +156,30 @@ class DeviceCosmo:
         self.ctx.check(lib().bolt_plin(self.ctx._h, self._h, abi.ptr(k), len(k), C.byref(opts), abi.ptr(pk),
                                        abi.ptr(st, abi.c_int32_p), abi.ptr(ns, abi.c_int64_p)))
         return pk, st, ns
+
+    # ---- device-pointer variants (torch tensors own the HBM buffers) ---------------------------------
+    def solve_device(self, k_t, opts, want_final=False):
+        """k_t: float64 CUDA tensor [nk].  Returns CUDA tensors S_T, S_P [nk][n_x], status, nsteps."""
+        import torch
+        nk, n_x = k_t.numel(), self.hc.n_x
+        dev = k_t.device
+        S_T = torch.zeros((nk, n_x), dtype=torch.float64, device=dev)
+        S_P = torch.zeros((nk, n_x), dtype=torch.float64, device=dev)
+        status = torch.zeros(nk, dtype=torch.int32, device=dev)
+        nsteps = torch.zeros(nk, dtype=torch.int64, device=dev)
+        n = abi.state_dim(opts.l_gamma, opts.l_nu, opts.l_mnu, self.hc.nq)
+        u_final = torch.zeros((nk, n), dtype=torch.float64, device=dev) if want_final else None
+        torch.cuda.current_stream(dev).synchronize()
+        self.ctx.check(lib().bolt_solve_device(self.ctx._h, self._h, k_t.data_ptr(), nk, C.byref(opts), S_T.data_ptr(), S_P.data_ptr(),
+                                               u_final.data_ptr() if want_final else None, status.data_ptr(), nsteps.data_ptr(), None))
+        return S_T, S_P, status, nsteps, u_final
+
+    def project_device(self, S_T, S_P, k_t, ells, kd_min, kd_max, n_kd, ix_start):
+        """S_T, S_P: float64 CUDA tensors [nk][n_x]; returns a CUDA tensor [3][nell] (tt, te, ee)."""
+        import torch
+        ells = np.ascontiguousarray(ells, dtype=np.int32)
+        cl = torch.zeros((3, len(ells)), dtype=torch.float64, device=k_t.device)
+        torch.cuda.current_stream(k_t.device).synchronize()
+        self.ctx.check(lib().bolt_project_device(self.ctx._h, self._h, S_T.data_ptr(), S_P.data_ptr(), k_t.data_ptr(), k_t.numel(),
+                                                 abi.ptr(ells, abi.c_int32_p), len(ells), kd_min, kd_max, n_kd, ix_start, cl.data_ptr()))
+        return cl

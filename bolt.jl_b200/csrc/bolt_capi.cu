@@ -29,6 +29,17 @@ struct bolt_cosmo {
   double* d_tables = nullptr;
 };
 
+// DFMA throughput microbenchmark: 8 independent FMA chains per thread (the FP64 roofline denominator;
+// MEASURED_PEAKS.json carries no FP64 figure).
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
 namespace {
 
 int fail(bolt_ctx* ctx, int code, const std::string& msg) {
@@ -121,6 +132,77 @@ int collect_timing(bolt_ctx* ctx) {
   return BOLT_OK;
 }
 void reset_timing(bolt_ctx* ctx) { for (int i = 0; i < 8; i++) ctx->timing[i] = 0; }
+
+constexpr int PROJ_NL = 4, PROJ_NT = 512;
+
+// K2 pipeline on device buffers.  d_cl = [3][nell] (tt, te, ee).
+int project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, const double* d_SP, const double* d_kc, int nk,
+                   const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start, double* d_cl) {
+  const DevCosmo& h = c->h;
+  if (n_kd < 2 || ix_start < 0 || ix_start >= h.n_x - 1) return fail(ctx, BOLT_ERR_ARG, "bad dense grid / ix_start");
+  for (int i = 0; i < nell; i++) {
+    if (ell[i] < 0) return fail(ctx, BOLT_ERR_ARG, "negative multipole");
+    if (i > 0 && ell[i] <= ell[i - 1]) return fail(ctx, BOLT_ERR_ARG, "multipoles must be strictly increasing");
+  }
+  const int nrows = h.n_x - 1 - ix_start;           // x_grid[ix_start .. n_x-2] (spectra.jl:70-76)
+  const int nkd1 = n_kd - 1;
+  const int ld = (nkd1 + 31) / 32 * 32;
+  const double xmax = kd_max * h.s[BOLT_S_eta0];    // kgrid[end]*eta0 (spectra.jl:85); quadratic_k ends exactly at kmax
+  const double dg = xmax / 5000.0;
+  DevBuf<int> d_ell, d_jlo; DevBuf<double> d_J, d_Cf, d_cp, d_iden, d_ks, d_wk, d_wl, d_chi, d_SDT, d_SDP, d_part;
+  CUDA_OK(d_ell.alloc(nell)); CUDA_OK(d_J.alloc((size_t)nell * BESSEL_NB)); CUDA_OK(d_Cf.alloc((size_t)nell * BESSEL_NC));
+  CUDA_OK(cudaMemcpyAsync(d_ell.p, ell, nell * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  {  // Thomas multipliers of the (1/6, 2/3, 1/6) interior system
+    const int m = BESSEL_NB - 2; std::vector<double> cp(m), iden(m);
+    const double a = 1.0 / 6.0, b = 2.0 / 3.0;
+    for (int i = 0; i < m; i++) { const double den = (i == 0) ? b : b - a * cp[i - 1]; cp[i] = a / den; iden[i] = 1.0 / den; }
+    CUDA_OK(d_cp.alloc(m)); CUDA_OK(d_iden.alloc(m));
+    CUDA_OK(cudaMemcpyAsync(d_cp.p, cp.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(d_iden.p, iden.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  bessel_table_kernel<<<(BESSEL_NB + 63) / 64, 64, 0, ctx->stream>>>(d_ell.p, nell, dg, d_J.p);
+  CUDA_OK(cudaGetLastError());
+  bessel_prefilter_kernel<<<(nell + 31) / 32, 32, 0, ctx->stream>>>(d_J.p, nell, d_cp.p, d_iden.p, d_Cf.p);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timing[5] += 2;
+  CUDA_OK(d_ks.alloc(nkd1)); CUDA_OK(d_wk.alloc(nkd1)); CUDA_OK(d_wl.alloc(nkd1)); CUDA_OK(d_jlo.alloc(nkd1)); CUDA_OK(d_chi.alloc(nrows));
+  CUDA_OK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  dense_k_kernel<<<(nkd1 + 127) / 128, 128, 0, ctx->stream>>>(d_kc, nk, kd_min, kd_max, n_kd, h.s[BOLT_S_A], h.s[BOLT_S_n], dg,
+                                                              d_ks.p, d_wk.p, d_jlo.p, d_wl.p);
+  CUDA_OK(cudaGetLastError());
+  chi_kernel<<<(nrows + 127) / 128, 128, 0, ctx->stream>>>(c->d, ix_start, nrows, d_chi.p);
+  CUDA_OK(cudaGetLastError());
+  dim3 gsd((nkd1 + 127) / 128, nrows);
+  if (d_ST) { CUDA_OK(d_SDT.alloc((size_t)nrows * ld));
+    dense_source_kernel<<<gsd, 128, 0, ctx->stream>>>(d_ST, h.n_x, ix_start, nrows, d_jlo.p, d_wl.p, nkd1, ld, h.x0, h.dx, d_SDT.p);
+    CUDA_OK(cudaGetLastError()); ctx->timing[6] += 1; }
+  if (d_SP) { CUDA_OK(d_SDP.alloc((size_t)nrows * ld));
+    dense_source_kernel<<<gsd, 128, 0, ctx->stream>>>(d_SP, h.n_x, ix_start, nrows, d_jlo.p, d_wl.p, nkd1, ld, h.x0, h.dx, d_SDP.p);
+    CUDA_OK(cudaGetLastError()); ctx->timing[6] += 1; }
+  const int groups = (nell + PROJ_NL - 1) / PROJ_NL;
+  int nsplit = (8 * ctx->num_sms + groups - 1) / groups;
+  nsplit = std::max(1, std::min(nsplit, std::max(1, nkd1 / PROJ_NT)));
+  CUDA_OK(d_part.alloc((size_t)nell * nsplit * 3));
+  ProjectParams pp;
+  pp.Cf = d_Cf.p; pp.ells = d_ell.p; pp.nell = nell; pp.chi = d_chi.p; pp.nrows = nrows; pp.kscaled = d_ks.p; pp.wk = d_wk.p;
+  pp.nkd1 = nkd1; pp.ld = ld; pp.SD_T = d_SDT.p; pp.SD_P = d_SDP.p; pp.nsplit = nsplit; pp.partial = d_part.p;
+  const size_t smem = ((size_t)PROJ_NL * BESSEL_NC + nrows) * sizeof(double);
+  CUDA_OK(cudaFuncSetAttribute(project_kernel<PROJ_NL, PROJ_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_kernel<PROJ_NL, PROJ_NT><<<dim3(groups, nsplit), PROJ_NT, smem, ctx->stream>>>(pp);
+  CUDA_OK(cudaGetLastError());
+  cl_finalize_kernel<<<(nell + 127) / 128, 128, 0, ctx->stream>>>(d_part.p, d_ell.p, nell, nsplit, d_ST ? d_cl : nullptr,
+                                                                  (d_ST && d_SP) ? d_cl + nell : nullptr,
+                                                                  d_SP ? d_cl + 2 * (size_t)nell : nullptr);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->timing[6] += 4;
+  // the DevBufs above are freed on return: wait for the stream first
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return BOLT_OK;
+}
 
 }  // namespace
 
@@ -255,12 +337,141 @@ int bolt_solve(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, cons
   return collect_timing(ctx);
 }
 
-// --- not yet implemented in this build step -------------------------------------------------------
-int bolt_project(bolt_ctx* ctx, const bolt_cosmo*, const double*, const double*, const double*, int, const int32_t*, int,
-                 double, double, int, int, double*, double*, double*) { return fail(ctx, BOLT_ERR_UNSUPPORTED, "bolt_project: pending"); }
-int bolt_spectra(bolt_ctx* ctx, const bolt_cosmo*, const double*, int, const bolt_opts*, const int32_t*, int, double, double,
-                 int, int, double*, double*, double*, int32_t*, int64_t*) { return fail(ctx, BOLT_ERR_UNSUPPORTED, "bolt_spectra: pending"); }
-int bolt_plin(bolt_ctx* ctx, const bolt_cosmo*, const double*, int, const bolt_opts*, double*, int32_t*, int64_t*) {
-  return fail(ctx, BOLT_ERR_UNSUPPORTED, "bolt_plin: pending"); }
+int bolt_project(bolt_ctx* ctx, const bolt_cosmo* c, const double* S_T, const double* S_P, const double* k, int nk,
+                 const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start,
+                 double* cl_tt, double* cl_te, double* cl_ee) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (!c || !k || nk < 2 || !ell || nell < 1 || (!S_T && !S_P)) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
+  if (c->h.nd != 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "dual partials (nd > 1) are not implemented in this build");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  reset_timing(ctx);
+  CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const int n_x = c->h.n_x;
+  DevBuf<double> d_k, d_ST, d_SP, d_cl;
+  CUDA_OK(d_k.alloc(nk));
+  CUDA_OK(cudaMemcpyAsync(d_k.p, k, nk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (S_T) { CUDA_OK(d_ST.alloc((size_t)nk * n_x)); CUDA_OK(cudaMemcpyAsync(d_ST.p, S_T, d_ST.n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
+  if (S_P) { CUDA_OK(d_SP.alloc((size_t)nk * n_x)); CUDA_OK(cudaMemcpyAsync(d_SP.p, S_P, d_SP.n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
+  CUDA_OK(d_cl.alloc((size_t)3 * nell));
+  int rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, ell, nell, kd_min, kd_max, n_kd, ix_start, d_cl.p);
+  if (rc) return rc;
+  if (cl_tt && S_T) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_te && S_T && S_P) CUDA_OK(cudaMemcpyAsync(cl_te, d_cl.p + nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_ee && S_P) CUDA_OK(cudaMemcpyAsync(cl_ee, d_cl.p + 2 * (size_t)nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return collect_timing(ctx);
+}
+
+int bolt_spectra(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
+                 const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start,
+                 double* cl_tt, double* cl_te, double* cl_ee, int32_t* status, int64_t* nsteps) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (!c || !k || nk < 2 || !ell || nell < 1) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
+  int rc = check_opts(ctx, c, o); if (rc) return rc;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  reset_timing(ctx);
+  CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const int n_x = c->h.n_x;
+  DevBuf<double> d_k, d_ST, d_SP, d_cl; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns;
+  rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
+  CUDA_OK(d_ST.alloc((size_t)nk * n_x)); CUDA_OK(d_SP.alloc((size_t)nk * n_x));
+  CUDA_OK(d_status.alloc(nk)); CUDA_OK(d_ns.alloc(nk)); CUDA_OK(d_cl.alloc((size_t)3 * nell));
+  bolt_opts oo = *o;
+  oo.ix_first = std::max(oo.ix_first, ix_start);    // the LOS sum only reads rows >= ix_start (spectra.jl:86)
+  rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, d_ST.p, d_SP.p, nullptr, nullptr, d_status.p, d_ns.p, nullptr);
+  if (rc) return rc;
+  rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, ell, nell, kd_min, kd_max, n_kd, ix_start, d_cl.p);
+  if (rc) return rc;
+  if (cl_tt) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_te) CUDA_OK(cudaMemcpyAsync(cl_te, d_cl.p + nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_ee) CUDA_OK(cudaMemcpyAsync(cl_ee, d_cl.p + 2 * (size_t)nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, d_status.p, nk * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nsteps) CUDA_OK(cudaMemcpyAsync(nsteps, d_ns.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return collect_timing(ctx);
+}
+
+int bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o, double* pk, int32_t* status,
+              int64_t* nsteps) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (!c || !k || nk < 1 || !pk) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
+  int rc = check_opts(ctx, c, o); if (rc) return rc;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  reset_timing(ctx);
+  CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const int n = bolt_state_dim(o->l_gamma, o->l_nu, o->l_mnu, c->h.nq);
+  DevBuf<double> d_k, d_final, d_pk; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns;
+  rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
+  CUDA_OK(d_final.alloc((size_t)nk * n)); CUDA_OK(d_pk.alloc(nk)); CUDA_OK(d_status.alloc(nk)); CUDA_OK(d_ns.alloc(nk));
+  bolt_opts oo = *o; oo.ix_first = c->h.n_x;   // plin only needs perturb(0): no source sampling
+  rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, nullptr, nullptr, nullptr, d_final.p, d_status.p, d_ns.p, nullptr);
+  if (rc) return rc;
+  plin_kernel<<<(nk + 127) / 128, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(pk, d_pk.p, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, d_status.p, nk * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nsteps) CUDA_OK(cudaMemcpyAsync(nsteps, d_ns.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return collect_timing(ctx);
+}
+
+int bolt_solve_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, int nk, const bolt_opts* o,
+                      double* d_S_T, double* d_S_P, double* d_u_final, int32_t* d_status, int64_t* d_nsteps, int64_t* d_nreject) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (!c || !d_k || nk < 1) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
+  int rc = check_opts(ctx, c, o); if (rc) return rc;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  reset_timing(ctx);
+  CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  std::vector<double> hk(nk);
+  CUDA_OK(cudaMemcpyAsync(hk.data(), d_k, nk * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  DevBuf<double> d_k2; DevBuf<int> d_order;
+  rc = upload_k_sorted(ctx, hk.data(), nk, d_k2, d_order); if (rc) return rc;
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  rc = launch_hierarchy(ctx, c, d_k, d_order.p, nk, o, d_S_T, d_S_P, nullptr, d_u_final, d_status, (long long*)d_nsteps, (long long*)d_nreject);
+  if (rc) return rc;
+  CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return collect_timing(ctx);
+}
+
+int bolt_project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_S_T, const double* d_S_P, const double* d_k, int nk,
+                        const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start, double* d_cl) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (!c || !d_k || nk < 2 || !ell || nell < 1 || (!d_S_T && !d_S_P) || !d_cl) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
+  if (c->h.nd != 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "dual partials (nd > 1) are not implemented in this build");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  reset_timing(ctx);
+  CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  int rc = project_device(ctx, c, d_S_T, d_S_P, d_k, nk, ell, nell, kd_min, kd_max, n_kd, ix_start, d_cl);
+  if (rc) return rc;
+  CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return collect_timing(ctx);
+}
+
+int bolt_fp64_peak(bolt_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return BOLT_ERR_ARG;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  const int blocks = ctx->num_sms * 8, threads = 256, iters = 1 << 15;
+  DevBuf<double> d_out; CUDA_OK(d_out.alloc((size_t)blocks * threads));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out.p, iters, 0.999999, 1e-9);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  *tflops = best;
+  return BOLT_OK;
+}
 
 }  // extern "C"

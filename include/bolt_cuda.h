@@ -69,8 +69,7 @@ typedef struct bolt_opts {
 
 enum bolt_status {
   BOLT_OK = 0,
-  BOLT_ERR_ARG = -1, BOLT_ERR_CUDA = -2, BOLT_ERR_ALLOC = -3, BOLT_ERR_UNSUPPORTED = -4,
-  BOLT_ERR_NCCL = -5
+  BOLT_ERR_ARG = -1, BOLT_ERR_CUDA = -2, BOLT_ERR_ALLOC = -3, BOLT_ERR_UNSUPPORTED = -4
 };
 /* per-k status[] values */
 enum bolt_k_status { BOLT_K_OK = 0, BOLT_K_MAXSTEPS = 1, BOLT_K_DT_UNDERFLOW = 2,
@@ -131,9 +130,21 @@ int  bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, cons
  * out[4..7] = launch counts of the same. */
 int  bolt_last_timing(const bolt_ctx* ctx, double* out8);
 
-/* Multi-GPU: join an NCCL communicator created by the host (one rank per process);
- * afterwards bolt_spectra shards k-modes over ranks and all-reduces partial C_l. */
-int  bolt_comm_init(bolt_ctx* ctx, int rank, int nranks, const void* nccl_unique_id_128B);
+/* Measured DFMA throughput of the device (TFLOP/s): the FP64 roofline denominator. */
+int  bolt_fp64_peak(bolt_ctx* ctx, double* tflops);
+
+/* Device-pointer variants for callers that own HBM buffers (e.g. torch tensors exchanged with NCCL when the
+ * k-modes of ONE cosmology are sharded over GPUs: solve local k -> all-gather S_T,S_P -> project local l ->
+ * all-reduce C_l).  Same semantics as bolt_solve / bolt_project, every array argument except `ell` is a
+ * DEVICE pointer on the context's device; status/nsteps/nreject use int32/int64 device arrays.  The calls
+ * run on the context's stream and return after it has drained. */
+int  bolt_solve_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, int nk, const bolt_opts* o,
+                       double* d_S_T, double* d_S_P, double* d_u_final,
+                       int32_t* d_status, int64_t* d_nsteps, int64_t* d_nreject);
+int  bolt_project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_S_T, const double* d_S_P,
+                         const double* d_k, int nk, const int32_t* ell, int nell,
+                         double kd_min, double kd_max, int n_kd, int ix_start,
+                         double* d_cl /* [3][nell]: tt, te, ee */);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,60 @@
+"""Regenerates tests/golden/*.npz.  Run in the build container (needs /root/reference/test/data):
+
+    python tests/golden/make_golden.py
+
+1. Reference fixtures, subsampled so they stay small (provenance: xzackli/Bolt.jl test/data):
+   recfast_xe.npz      test_recfast_1.dat (Fortran RECFAST z, Xe)          -> test/runtests.jl:38-48
+   class_px.npz        zack_N_class_px_k{p03,p1}_nofluid_nonu.dat (x, phi, d_b) -> test/runtests.jl:83-147
+   camb_cl.npz         camb_rough_ttteee_unlensed.dat at l = 10:10:2500   -> test/runtests.jl:149-185
+2. Oracle outputs for the BASELINE C1 configuration (default CosmoParams, 100 quadratic k-modes, l_gamma = 8,
+   reltol 1e-11): source grids on the LOS rows and C_l -- the vectors the GPU tests compare against without
+   re-running the slow CPU solve.
+"""
+import os, sys, time
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+REF = "/root/reference/test/data"
+
+
+def reference_fixtures():
+    d = np.loadtxt(f"{REF}/test_recfast_1.dat", delimiter=",", skiprows=1, usecols=(0, 1))
+    d = d[:-5][::7]                                   # runtests.jl:41 drops the last 5 rows
+    np.savez_compressed(f"{HERE}/recfast_xe.npz", z=d[:, 0], Xe=d[:, 1])
+    out = {}
+    for tag in ("p03", "p1"):
+        c = np.loadtxt(f"{REF}/zack_N_class_px_k{tag}_nofluid_nonu.dat")
+        sel = np.arange(0, c.shape[1], 4)
+        out[f"x_{tag}"] = c[0, sel]; out[f"k_{tag}"] = c[1, 0]
+        out[f"d_b_{tag}"] = c[3, sel]; out[f"phi_{tag}"] = c[7, sel]
+    np.savez_compressed(f"{HERE}/class_px.npz", **out)
+    camb = np.loadtxt(f"{REF}/camb_rough_ttteee_unlensed.dat")
+    ells = np.arange(10, 2501, 10)
+    np.savez_compressed(f"{HERE}/camb_cl.npz", ell=ells, tt=np.interp(ells, camb[0], camb[1]),
+                        te=np.interp(ells, camb[0], camb[2]), ee=np.interp(ells, camb[0], camb[3]))
+
+
+def oracle_vectors():
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    from oracle.oracle import OracleCosmo
+    par = B.CosmoParams(); bg = B.Background(par)
+    ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+    hc = abi.HostCosmo.from_host(par, bg, ih); oc = OracleCosmo(hc)
+    kg = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 100)
+    o = abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6)
+    t = time.time(); out = oc.solve(kg, o, want=("S_T", "S_P")); print("oracle solve %.1fs" % (time.time() - t))
+    ix_start = int(np.argmax(bg.x_grid > -8))
+    ells = np.arange(10, 2501, 10)
+    tt, te, ee = oc.project(out["S_T"], out["S_P"], kg, ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, ix_start)
+    np.savez_compressed(f"{HERE}/oracle_c1.npz", k=kg, ix_start=ix_start, S_T=out["S_T"][:, ix_start:], S_P=out["S_P"][:, ix_start:],
+                        nsteps=out["nsteps"], nreject=out["nreject"], ell=ells, tt=tt, te=te, ee=ee,
+                        tables=hc.tables, scalars=hc.scalars, quad_pts=hc.quad_pts, quad_wts=hc.quad_wts, x0=hc.x0, dx=hc.dx)
+
+
+if __name__ == "__main__":
+    reference_fixtures()
+    oracle_vectors()
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))

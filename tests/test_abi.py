@@ -1,0 +1,70 @@
+"""The C-ABI library loads and exports every symbol include/bolt_cuda.h declares; struct layouts match ctypes."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "bolt_cuda.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bolt_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from bolt_b200 import capi
+    lib = C.CDLL(capi.LIB_PATH)
+    names = declared_functions()
+    assert {"bolt_init", "bolt_solve", "bolt_project", "bolt_spectra", "bolt_plin", "bolt_cosmo_upload"} <= set(names)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.bolt_abi_version() == 1
+    assert lib.bolt_state_dim(8, 8, 10, 15) == 197 and lib.bolt_state_dim(50, 50, 20, 15) == 473
+
+
+def test_struct_layout_matches_header(tmp_path):
+    from bolt_b200 import abi
+    prog = tmp_path / "layout.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bolt_cuda.h"\n'
+                    'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(bolt_cosmo_desc), offsetof(bolt_cosmo_desc,x0),'
+                    'offsetof(bolt_cosmo_desc,scalars), offsetof(bolt_cosmo_desc,tables), sizeof(bolt_opts), offsetof(bolt_opts,reltol),'
+                    'offsetof(bolt_opts,max_steps), offsetof(bolt_opts,ix_first), (int)BOLT_NSCALARS, (int)BOLT_NTABLES);return 0;}\n')
+    exe = tmp_path / "layout"
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    D, O = abi.CosmoDesc, abi.Opts
+    want = [C.sizeof(D), D.x0.offset, D.scalars.offset, D.tables.offset, C.sizeof(O), O.reltol.offset, O.max_steps.offset,
+            O.ix_first.offset, abi.NSCALARS, abi.NTABLES]
+    assert got == want
+
+
+def test_no_cpu_fallback_without_device():
+    """The product path must fail loudly when there is no usable GPU."""
+    import torch
+    from bolt_b200 import capi
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(capi.BoltError):
+        capi.Context(0)
+    import bolt_b200 as B
+    with pytest.raises(capi.BoltError):
+        B.default_context()
+
+
+def test_product_does_not_import_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "bolt.jl_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".jl")):
+                txt = open(os.path.join(d, f)).read()
+                assert "oracle" not in txt.replace("oracle does the same", "").replace("the oracle", "").replace("as the oracle", "").lower() \
+                    or "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f

@@ -1,0 +1,71 @@
+"""The reference-interface mirror on the GPU, written like the reference's own tests (test/runtests.jl)."""
+import numpy as np
+import pytest
+from scipy.interpolate import CubicSpline
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cell_camb_1e_1(cosmo):
+    """test/runtests.jl:149-185 ("cell_camb_1e-1") through the drop-in API."""
+    import bolt_b200 as B
+    par, bg, ih = cosmo.par, cosmo.bg, cosmo.ih
+    k_grid = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 100)
+    sf_t = B.source_grid(par, bg, ih, k_grid, B.BasicNewtonian())
+    sf_e = B.source_grid_P(par, bg, ih, k_grid, B.BasicNewtonian())
+    ells = np.arange(10, 2501, 10)
+    lfac = ells * (ells + 1) / (2 * np.pi)
+    Ctt = B.cltt(ells, par, bg, ih, sf_t)
+    Cte = B.clte(ells, par, bg, ih, sf_t, sf_e)
+    Cee = B.clee(ells, par, bg, ih, sf_e)
+    camb = load_golden("camb_cl.npz")
+    TOL = 1.1e-1
+    assert np.all(np.abs(lfac * Ctt / camb["tt"] - 1) < TOL)
+    assert np.all(np.abs(lfac * Cee / camb["ee"] - 1) < TOL)
+    assert np.all(Cte ** 2 <= Ctt * Cee * (1 + 1e-12))
+    # scalar-ℓ methods and the (ℓ, s_itp, kgrid, par, bg) method give the same numbers
+    assert B.cltt(500, par, bg, ih, sf_t) == pytest.approx(Ctt[49], rel=1e-12)
+    dense = B.quadratic_k(0.01 * bg.H0, 1000 * bg.H0, 5000)
+    assert B.clee(500, sf_e, dense, par, bg, ih=ih) == pytest.approx(Cee[49], rel=1e-9)
+    # the interpolant is callable like the reference's itp(x, k)
+    assert sf_t(-7.0, k_grid[10]) == pytest.approx(sf_t.grid[1300, 10], rel=1e-12)
+
+
+def test_nonu_class_comparison_1e_3(cosmo_nonu):
+    """test/runtests.jl:83-147 through boltsolve_rsa on the device."""
+    import bolt_b200 as B
+    c = cosmo_nonu
+    g = load_golden("class_px.npz")
+    for tag in ("p03", "p1"):
+        k = c.par.h * float(g[f"k_{tag}"])
+        h = B.Hierarchy(B.BasicNewtonian(), c.par, c.bg, c.ih, k, 50, 50, 20, 15)
+        res = B.boltsolve_rsa(h, reltol=1e-9, abstol=1e-9)
+        n = res.shape[0]
+        cx = g[f"x_{tag}"][::-1]
+        phi = CubicSpline(c.bg.x_grid, res[n - 5])(cx)
+        d_b = CubicSpline(c.bg.x_grid, res[n - 2])(cx)
+        assert np.all(np.abs(phi / g[f"phi_{tag}"][::-1] - 1) < 1e-3), tag
+        assert np.all(np.abs(-d_b / g[f"d_b_{tag}"][::-1] - 1) < 1e-3), tag
+
+
+def test_plin_scalar_and_vector(cosmo):
+    """examples/basic_usage.jl:11-14: pL = [plin(k, 𝕡, bg, ih) for k in ks]."""
+    import bolt_b200 as B
+    par, bg, ih = cosmo.par, cosmo.bg, cosmo.ih
+    ks = B.log10_k(10 * bg.H0, 5000 * bg.H0, 8)
+    pv = B.plin(ks, par, bg, ih)
+    assert pv.shape == (8,) and np.all(pv > 0)
+    assert B.plin(float(ks[3]), par, bg, ih) == pytest.approx(pv[3], rel=1e-12)
+    # P(k) turns over: rises then falls across the equality scale
+    assert pv.argmax() not in (0, 7)
+
+
+def test_boltsolve_solution_is_callable(cosmo):
+    import bolt_b200 as B
+    h = B.Hierarchy(B.BasicNewtonian(), cosmo.par, cosmo.bg, cosmo.ih, 30 * cosmo.bg.H0)
+    sol = B.boltsolve(h, reltol=1e-8)
+    assert sol.retcode == 0 and sol(-20.0).shape == (197,) and sol.u.shape == (2001, 197)
+    u0 = sol(-20.0)
+    assert u0[-4] == u0[-2] == 3 * u0[0]          # adiabatic ICs (perturbations.jl:308-312)

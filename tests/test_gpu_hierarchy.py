@@ -1,0 +1,95 @@
+"""K1 parity (through the C ABI) against the CPU oracle and the committed oracle vectors."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def hist_err(a, b):
+    """max |a-b| relative to each variable's own maximum over the history."""
+    sc = np.abs(b).max(axis=0) + 1e-300
+    return (np.abs(a - b) / sc).max()
+
+
+@pytest.mark.parametrize("trunc,dt,kfac", [((8, 8, 10), 0.005, [0.3, 30.0, 400.0]),
+                                           ((10, 8, 10), 0.01, [5.0]),
+                                           ((12, 9, 7), 0.01, [60.0])])
+def test_fixed_step_histories_match_oracle(cosmo, oracle, dev, trunc, dt, kfac):
+    """north_star: in fixed-step mode per-k perturbation histories agree within 1e-8 relative."""
+    from bolt_b200 import abi
+    o = abi.make_opts(*trunc, fixed_dt=dt)
+    ks = np.array(kfac) * cosmo.bg.H0
+    g = dev.solve(ks, o, want=("S_T", "S_P", "u_hist", "u_final"))
+    r = oracle.solve(ks, o, want=("S_T", "S_P", "u_hist", "u_final"))
+    assert np.all(g["status"] == 0) and np.array_equal(g["nsteps"], r["nsteps"])
+    for i in range(len(ks)):
+        assert hist_err(g["u_hist"][i], r["u_hist"][i]) < 1e-8
+        assert np.abs(g["u_final"][i] - r["u_final"][i]).max() < 1e-8 * np.abs(r["u_final"][i]).max()
+        for key in ("S_T", "S_P"):
+            a, b = g[key][i, :-1], r[key][i, :-1]          # last S_P row is ±Inf by construction
+            assert np.abs(a - b).max() < 1e-8 * np.abs(b).max()
+
+
+def test_fixed_step_plin_truncation(cosmo, oracle, dev):
+    """n = 473 (ℓᵧ = ℓ_ν = 50, ℓ_mν = 20): the plin / CLASS-test state size."""
+    from bolt_b200 import abi
+    o = abi.make_opts(50, 50, 20, fixed_dt=0.02)
+    ks = np.array([40.0]) * cosmo.bg.H0
+    g = dev.solve(ks, o, want=("u_hist",)); r = oracle.solve(ks, o, want=("u_hist",))
+    assert g["status"][0] == 0
+    assert hist_err(g["u_hist"][0], r["u_hist"][0]) < 1e-8
+
+
+def test_adaptive_sources_match_golden_c1(cosmo, dev):
+    """BASELINE config 1 (100 quadratic k-modes, ℓᵧ = 8, reltol 1e-11): source grids vs the committed oracle output."""
+    from bolt_b200 import abi
+    g = load_golden("oracle_c1.npz")
+    ix0 = int(g["ix_start"])
+    o = abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6)
+    out = dev.solve(g["k"], o, want=("S_T", "S_P"))
+    assert np.all(out["status"] == 0)
+    # same controller, same arithmetic up to rounding: step counts agree (allow a stray accept/reject flip)
+    assert np.abs(out["nsteps"] - g["nsteps"]).max() <= 2
+    for key in ("S_T", "S_P"):
+        a, b = out[key][:, ix0:-1], g[key][:, :-1]
+        err = np.abs(a - b).max(axis=1) / np.abs(b).max(axis=1)
+        assert err.max() < 1e-5, (key, err.argmax(), err.max())
+    assert not np.isfinite(out["S_P"][:, -1]).any()        # y = 0 at x = 0 (perturbations.jl:401-403)
+
+
+def test_ix_first_skips_early_rows(cosmo, dev):
+    from bolt_b200 import abi
+    ks = np.array([10.0, 200.0]) * cosmo.bg.H0
+    full = dev.solve(ks, abi.make_opts(8, 8, 10, reltol=1e-8, abstol=1e-6), want=("S_T",))
+    part = dev.solve(ks, abi.make_opts(8, 8, 10, reltol=1e-8, abstol=1e-6, ix_first=1201), want=("S_T",))
+    assert np.all(part["S_T"][:, :1201] == 0)
+    assert np.array_equal(part["S_T"][:, 1201:], full["S_T"][:, 1201:])
+
+
+def test_deterministic_and_order_independent(cosmo, dev):
+    from bolt_b200 import abi
+    o = abi.make_opts(8, 8, 10, reltol=1e-9, abstol=1e-6)
+    ks = np.array([3.0, 700.0, 50.0, 120.0]) * cosmo.bg.H0
+    a = dev.solve(ks, o, want=("S_T",)); b = dev.solve(ks[::-1].copy(), o, want=("S_T",))
+    assert np.array_equal(a["S_T"], b["S_T"][::-1]) and np.array_equal(a["nsteps"], b["nsteps"][::-1])
+
+
+def test_max_steps_and_bad_arguments(cosmo, dev):
+    from bolt_b200 import abi, capi
+    ks = np.array([500.0]) * cosmo.bg.H0
+    out = dev.solve(ks, abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6, max_steps=50), want=("u_final",))
+    assert out["status"][0] == abi.K_MAXSTEPS and out["nsteps"][0] + out["nreject"][0] == 50
+    with pytest.raises(capi.BoltError):
+        dev.solve(ks, abi.make_opts(2, 8, 10), want=("u_final",))           # ℓᵧ < 3: source_function needs Θ₃
+    with pytest.raises(capi.BoltError):
+        dev.solve(ks, abi.make_opts(8, 8, 10, reltol=0.0), want=("u_final",))
+
+
+def test_rsa_flagged_for_out_of_envelope_k(cosmo, dev):
+    """The in-RHS RSA switch (perturbations.jl:216) is outside the supported envelope of the implicit stages;
+    the kernel reports it instead of silently integrating something else."""
+    from bolt_b200 import abi
+    out = dev.solve(np.array([200.0]), abi.make_opts(8, 8, 10, fixed_dt=0.5), want=("u_final",))
+    assert out["status"][0] == abi.K_RSA_TRIGGERED
