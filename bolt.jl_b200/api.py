@@ -63,7 +63,7 @@ class Solution:
         self.t, self.u, self.retcode, self.nsteps = x_grid, u, int(status), int(nsteps)
 
     def __call__(self, x):
-        t = (x - self.t[0]) / (self.t[1] - self.t[0])
+        t = (x - self.t[0]) / ((self.t[-1] - self.t[0]) / (len(self.t) - 1))
         i = int(np.clip(np.floor(t), 0, len(self.t) - 2))
         w = t - i
         return (1 - w) * self.u[i] + w * self.u[i + 1]
@@ -144,7 +144,7 @@ class SourceInterpolant:
 
     def __call__(self, x, k):
         xg, kg = self.x_grid, self.k_grid
-        tx = (np.asarray(x, dtype=np.float64) - xg[0]) / (xg[1] - xg[0])
+        tx = (np.asarray(x, dtype=np.float64) - xg[0]) / ((xg[-1] - xg[0]) / (len(xg) - 1))
         ix = np.clip(np.floor(tx).astype(int), 0, len(xg) - 2); wx = tx - ix
         k = np.asarray(k, dtype=np.float64)
         jk = np.clip(np.searchsorted(kg, k, side="right") - 1, 0, len(kg) - 2)

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -21,7 +22,9 @@ struct bolt_ctx {
   std::string err;
   double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int* d_counter = nullptr;
+  double* d_dbg = nullptr;   // step log (only when BOLT_DEBUG_STEPS is set)
 };
+constexpr int DBG_CAP = 1 << 16;
 
 struct bolt_cosmo {
   DevCosmo h;              // host copy (table pointers are device pointers)
@@ -96,6 +99,7 @@ int launch_hierarchy(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, cons
   p.max_steps = o->max_steps; p.ix_first = o->ix_first;
   p.S_T = d_ST; p.S_P = d_SP; p.u_hist = d_hist; p.u_final = d_final;
   p.status = d_status; p.nsteps = d_nsteps; p.nreject = d_nreject; p.counter = ctx->d_counter;
+  p.dbg = ctx->d_dbg; p.dbg_cap = ctx->d_dbg ? DBG_CAP : 0;
   const size_t smem = (size_t)9 * p.n * sizeof(double);
   CUDA_OK(cudaFuncSetAttribute(hierarchy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_OK(cudaFuncSetAttribute(hierarchy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -228,6 +232,7 @@ int bolt_init(int device_ordinal, bolt_ctx** out) {
   for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
   if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return BOLT_ERR_ALLOC; }
   if (init_constants(ctx) != BOLT_OK) { delete ctx; return BOLT_ERR_CUDA; }
+  if (getenv("BOLT_DEBUG_STEPS")) { cudaMalloc(&ctx->d_dbg, sizeof(double) * 4 * DBG_CAP); cudaMemset(ctx->d_dbg, 0, sizeof(double) * 4 * DBG_CAP); }
   *out = ctx;
   return BOLT_OK;
 }
@@ -334,6 +339,14 @@ int bolt_solve(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, cons
   if (nreject) CUDA_OK(cudaMemcpyAsync(nreject, d_nr.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_dbg) {   // development aid: per-step log of mode 0
+    std::vector<double> h((size_t)4 * DBG_CAP);
+    cudaMemcpy(h.data(), ctx->d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(getenv("BOLT_DEBUG_STEPS"), "w")) {
+      for (int i = 0; i < DBG_CAP && h[4 * i + 1] != 0.0; i++) fprintf(f, "x=%.10g dt=%.4g EEst=%.17g acc=%d\n", h[4 * i], h[4 * i + 1], h[4 * i + 2], (int)h[4 * i + 3]);
+      fclose(f);
+    }
+  }
   return collect_timing(ctx);
 }
 

@@ -44,6 +44,8 @@ struct SolveParams {
   long long* nsteps;      // [nk]
   long long* nreject;     // [nk]
   int* counter;           // work queue head
+  double* dbg;            // optional step log of mode 0: [dbg_cap][4] = x, dt, EEst, accepted
+  int dbg_cap;
 };
 
 __constant__ double c_rl[MAX_L + 1];   // l/(2l+1)
@@ -685,8 +687,13 @@ __global__ void __launch_bounds__(32) hierarchy_kernel(SolveParams p) {
         solve(c, ln, bs, f, ib, r, (double*)nullptr, none);      // smooth_est: W^{-1} err with the last stage's W
         EEst = sqrt(sumsq_scaled(r, U, Z1) / n);
         if (!isfinite(EEst)) { status = BOLT_K_NONFINITE; break; }
-        q11 = pow(EEst, beta1);
+        // Controller input floored at 1e-6: below that the estimate is rounding noise of the stiff start-up phase and
+        // would make the step sequence implementation-dependent (DESIGN.md "controller"); acceptance uses the raw value.
+        q11 = pow(fmax(EEst, 1e-6), beta1);
         accept = EEst <= 1.0;
+        if (p.dbg && ik == 0 && ln.lane == 0 && nsteps + nreject < p.dbg_cap) {
+          double* d = p.dbg + 4 * (nsteps + nreject); d[0] = x; d[1] = dt; d[2] = EEst; d[3] = accept ? 1.0 : 0.0;
+        }
       }
       if (accept) {
         const bool last = fixed ? (fixed_left == 1) : clamped;

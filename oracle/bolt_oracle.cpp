@@ -457,9 +457,10 @@ void solve_mode(const Mode& h, const bolt_opts& o, bool skip_zeros, SolveOut& ou
       st.lu.solve(err.data());   // smooth_est: filter the estimate with W^{-1} of the last stage [dep-knowledge]
       EEst = rms_scaled(err.data(), u.data(), unew.data(), n, abstol, reltol);
       if (!std::isfinite(EEst)) { out.status = BOLT_K_NONFINITE; break; }
-      q11 = std::pow(EEst, beta1);
+      // controller input floored at 1e-6 (rounding-noise guard, same rule as the device kernel; DESIGN.md "controller")
+      q11 = std::pow(std::max(EEst, 1e-6), beta1);
       accept = EEst <= 1.0;
-      if (getenv("ORACLE_DEBUG")) fprintf(stderr, "x=%.10g dt=%.4g EEst=%.4g acc=%d\n", x, dt, EEst, (int)accept);
+      if (getenv("ORACLE_DEBUG")) fprintf(stderr, "x=%.10g dt=%.4g EEst=%.17g acc=%d\n", x, dt, EEst, (int)accept);
     }
     if (accept) {
       // dense output on [x, x+dt]: cubic Hermite with f_n = z1/dt, f_{n+1} = z6/dt (KenCarp4 non-split
