@@ -30,6 +30,7 @@ struct bolt_cosmo {
   DevCosmo h;              // host copy (table pointers are device pointers)
   DevCosmo* d = nullptr;   // device copy
   double* d_tables = nullptr;
+  const DevCosmo** d_list = nullptr;   // device array {d}: the 1-cosmology work list of K1
 };
 
 // DFMA throughput microbenchmark: 8 independent FMA chains per thread (the FP64 roofline denominator;
@@ -41,6 +42,12 @@ __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
     x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// eta(x_grid[end]) evaluated with the device's own spline arithmetic, so that y = k(eta_end - eta(x)) is exactly 0 in the
+// last row of S_P, as in the reference (perturbations.jl:401-403).
+__global__ void eta_end_kernel(DevCosmo* c) {
+  c->eta_end = spline_eval(c->tab[BOLT_T_eta], c->n_x, c->x0, c->dx, c->x0 + c->dx * (c->n_x - 1));
 }
 
 namespace {
@@ -87,33 +94,48 @@ int check_opts(bolt_ctx* ctx, const bolt_cosmo* c, const bolt_opts* o) {
   return BOLT_OK;
 }
 
-// Launch K1 on device buffers.
-int launch_hierarchy(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, const int* d_order, int nk, const bolt_opts* o,
-                     double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status, long long* d_nsteps,
-                     long long* d_nreject) {
+template <int MAXLEN, int NQ>
+int launch_k1(bolt_ctx* ctx, const SolveParams& p) {
+  auto kern = hierarchy_kernel_t<MAXLEN, NQ>;
+  const size_t smem = (size_t)k1_num_arrays<MAXLEN, NQ>() * k1_array_len<MAXLEN, NQ>(p.n) * sizeof(double);
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int occ = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+  if (occ < 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "state does not fit in shared memory");
+  const int grid = std::max(1, std::min(p.nk, occ * ctx->num_sms));
+  CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  kern<<<grid, 32, smem, ctx->stream>>>(p);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->timing[4] += 1;
+  return BOLT_OK;
+}
+
+// Launch K1 on device buffers.  cos_list: device array of ncos cosmology pointers; work item g (0 <= g < nk) belongs to
+// cosmology g / nk_per.
+int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int nk_per, const double* d_k, const int* d_order, int nk,
+                     const bolt_opts* o, double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status,
+                     long long* d_nsteps, long long* d_nreject) {
   SolveParams p;
-  p.cos = c->d; p.k = d_k; p.order = d_order; p.nk = nk;
+  p.cos_list = cos_list; p.nk_per = nk_per; p.k = d_k; p.order = d_order; p.nk = nk;
   p.L = o->l_gamma; p.Lnu = o->l_nu; p.Lm = o->l_mnu;
-  p.n = bolt_state_dim(p.L, p.Lnu, p.Lm, c->h.nq);
+  p.n = bolt_state_dim(p.L, p.Lnu, p.Lm, nq);
   p.mode = o->mode; p.reltol = o->reltol; p.abstol = o->abstol; p.fixed_dt = o->fixed_dt;
   p.max_steps = o->max_steps; p.ix_first = o->ix_first;
   p.S_T = d_ST; p.S_P = d_SP; p.u_hist = d_hist; p.u_final = d_final;
   p.status = d_status; p.nsteps = d_nsteps; p.nreject = d_nreject; p.counter = ctx->d_counter;
   p.dbg = ctx->d_dbg; p.dbg_cap = ctx->d_dbg ? DBG_CAP : 0;
-  const size_t smem = (size_t)9 * p.n * sizeof(double);
-  CUDA_OK(cudaFuncSetAttribute(hierarchy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_OK(cudaFuncSetAttribute(hierarchy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  int occ = 0;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hierarchy_kernel, 32, smem));
-  if (occ < 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "state does not fit in shared memory");
-  const int grid = std::max(1, std::min(nk, occ * ctx->num_sms));
-  CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-  CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  hierarchy_kernel<<<grid, 32, smem, ctx->stream>>>(p);
-  CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  ctx->timing[4] += 1;
-  return BOLT_OK;
+  const int maxlen = std::max(p.L, std::max(p.Lnu, p.Lm)) + 1;
+  const bool force_generic = getenv("BOLT_K1_GENERIC") != nullptr;     // development switch
+  if (!force_generic && nq == 15 && maxlen <= 11) return launch_k1<11, 15>(ctx, p);   // source_grid defaults (l_gamma <= 10)
+  return launch_k1<0, 0>(ctx, p);                                                      // any truncation (plin: 50, 50, 20)
+}
+int launch_hierarchy(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, const int* d_order, int nk, const bolt_opts* o,
+                     double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status, long long* d_nsteps,
+                     long long* d_nreject) {
+  return launch_hierarchy(ctx, c->d_list, c->h.nq, nk, d_k, d_order, nk, o, d_ST, d_SP, d_hist, d_final, d_status, d_nsteps, d_nreject);
 }
 
 int upload_k_sorted(bolt_ctx* ctx, const double* k, int nk, DevBuf<double>& d_k, DevBuf<int>& d_order) {
@@ -299,6 +321,10 @@ int bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* d, bolt_cosmo** out)
   }
   if (cudaMalloc(&c->d, sizeof(DevCosmo)) != cudaSuccess) { cudaFree(c->d_tables); delete c; return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc cosmo"); }
   cudaMemcpy(c->d, &h, sizeof(DevCosmo), cudaMemcpyHostToDevice);
+  eta_end_kernel<<<1, 1, 0, ctx->stream>>>(c->d);
+  cudaStreamSynchronize(ctx->stream);
+  if (cudaMalloc(&c->d_list, sizeof(DevCosmo*)) != cudaSuccess) { cudaFree(c->d); cudaFree(c->d_tables); delete c; return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc list"); }
+  cudaMemcpy(c->d_list, &c->d, sizeof(DevCosmo*), cudaMemcpyHostToDevice);
   *out = c;
   return BOLT_OK;
 }
@@ -306,7 +332,7 @@ int bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* d, bolt_cosmo** out)
 int bolt_cosmo_free(bolt_ctx* ctx, bolt_cosmo* c) {
   if (!c) return BOLT_OK;
   if (ctx) cudaSetDevice(ctx->device);
-  cudaFree(c->d); cudaFree(c->d_tables);
+  cudaFree(c->d); cudaFree(c->d_tables); cudaFree(c->d_list);
   delete c;
   return BOLT_OK;
 }

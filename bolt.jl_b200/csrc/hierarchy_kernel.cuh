@@ -27,8 +27,9 @@
 namespace bolt {
 
 struct SolveParams {
-  const DevCosmo* cos;
-  const double* k;        // [nk]
+  const DevCosmo* const* cos_list;   // [ncos] device pointers; work item g belongs to cosmology g / nk_per
+  int nk_per;
+  const double* k;        // [nk] (nk = ncos * nk_per)
   const int* order;       // [nk] work order (largest k first)
   int nk;
   int L, Lnu, Lm, n;
@@ -70,7 +71,8 @@ enum ChainKind { CH_M = 0, CH_T = 1, CH_P = 2, CH_N = 3, CH_IDLE = 4 };
 
 // Everything a lane needs to know about the warp's mode and its own chain.
 struct Lane {
-  int lane, kind, base, stride, len;   // chain element l is at base + l*stride
+  int lane, kind, base, stride, len;   // chain element l is at base + l*stride (internal shared-memory layout)
+  int rbase, rstride, riS;             // the same element in the reference's unpack order (outputs)
   int nq, L, iS, n, maxlen;
   double k;
   double q, df0, wq;                   // massive-neutrino lanes only
@@ -415,24 +417,25 @@ __device__ __forceinline__ void initial_conditions(const DevCosmo& c, const Lane
   const double T1 = 10.0 * C / (15.0 + 4.0 * f_nu) * (k * k * eta) / (3.0 * k);
   const double T2 = -8.0 * k / (15.0 * Hx * taup) * T1;
   const double N2 = -(k * k * eta * eta) / 15.0 * 1.0 / (1.0 + 2.0 / 5.0 * f_nu) * Phi / 2.0;
+  const int st = ln.stride;
   if (ln.kind == CH_T) {
-    u[ln.base] = T0; u[ln.base + 1] = T1; u[ln.base + 2] = T2;
+    u[ln.base] = T0; u[ln.base + st] = T1; u[ln.base + 2 * st] = T2;
     double prev = T2;
-    for (int l = 3; l < ln.len; l++) { prev = -(double)l / (2 * l + 1) * k / (Hx * taup) * prev; u[ln.base + l] = prev; }
+    for (int l = 3; l < ln.len; l++) { prev = -(double)l / (2 * l + 1) * k / (Hx * taup) * prev; u[ln.base + l * st] = prev; }
   } else if (ln.kind == CH_P) {
-    u[ln.base] = (5.0 / 4.0) * T2; u[ln.base + 1] = -k / (4.0 * Hx * taup) * T2;
-    double prev = (1.0 / 4.0) * T2; u[ln.base + 2] = prev;
-    for (int l = 3; l < ln.len; l++) { prev = -(double)l / (2 * l + 1) * k / (Hx * taup) * prev; u[ln.base + l] = prev; }
+    u[ln.base] = (5.0 / 4.0) * T2; u[ln.base + st] = -k / (4.0 * Hx * taup) * T2;
+    double prev = (1.0 / 4.0) * T2; u[ln.base + 2 * st] = prev;
+    for (int l = 3; l < ln.len; l++) { prev = -(double)l / (2 * l + 1) * k / (Hx * taup) * prev; u[ln.base + l * st] = prev; }
   } else if (ln.kind == CH_N) {
-    u[ln.base] = T0; u[ln.base + 1] = T1; u[ln.base + 2] = N2;
+    u[ln.base] = T0; u[ln.base + st] = T1; u[ln.base + 2 * st] = N2;
     double prev = N2;
-    for (int l = 3; l < ln.len; l++) { prev = k / ((2 * l + 1) * Hx) * prev; u[ln.base + l] = prev; }
+    for (int l = 3; l < ln.len; l++) { prev = k / ((2 * l + 1) * Hx) * prev; u[ln.base + l * st] = prev; }
   } else if (ln.kind == CH_M) {
     const double df0 = ln.df0;
     u[ln.base] = -T0 * df0;
-    u[ln.base + ln.stride] = -b.eq * T1 * df0;
-    double prev = -N2 * df0; u[ln.base + 2 * ln.stride] = prev;
-    for (int l = 3; l < ln.len; l++) { prev = b.qe * k / ((2 * l + 1) * Hx) * prev; u[ln.base + l * ln.stride] = prev; }
+    u[ln.base + st] = -b.eq * T1 * df0;
+    double prev = -N2 * df0; u[ln.base + 2 * st] = prev;
+    for (int l = 3; l < ln.len; l++) { prev = b.qe * k / ((2 * l + 1) * Hx) * prev; u[ln.base + l * st] = prev; }
   }
   if (ln.lane == 0) {
     const double delta = 3.0 / 4.0 * (4.0 * T0), v = -3.0 * k * T1;
@@ -464,8 +467,8 @@ __device__ __forceinline__ void sample_sources(const DevCosmo& c, const Lane& ln
   auto herm = [&](int idx) { return hm.c0 * u0[idx] + hm.c1 * u1[idx] + hm.d0 * (s1 * z1[idx]) + hm.d1 * z6[idx]; };
   if (p.u_hist) {
     double* out = p.u_hist + ((size_t)ik * c.n_x + ix) * ln.n;
-    for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; out[idx] = herm(idx); }
-    if (ln.lane < 5) out[ln.iS + ln.lane] = herm(ln.iS + ln.lane);
+    for (int l = 0; l < ln.len; l++) out[ln.rbase + l * ln.rstride] = herm(ln.base + l * ln.stride);
+    if (ln.lane < 5) out[ln.riS + ln.lane] = herm(ln.iS + ln.lane);
   }
   if (!p.S_T && !p.S_P) return;
   Bg b; eval_bg(c, ln, xs, b);
@@ -536,53 +539,250 @@ __device__ __forceinline__ void sample_sources(const DevCosmo& c, const Lane& ln
 // The kernel: persistent warps pull k-modes from a queue.
 // Shared memory per warp: 9 arrays of n doubles: u, z1..z6, work r, inverse pivots ib.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) hierarchy_kernel(SolveParams p) {
-  extern __shared__ double sm[];
-  const DevCosmo& c = *p.cos;
-  const int n = p.n;
-  Lane ln;
-  ln.lane = threadIdx.x; ln.nq = c.nq; ln.L = p.L; ln.n = n;
-  ln.iS = 2 * (p.L + 1) + (p.Lnu + 1) + (p.Lm + 1) * c.nq;
+// ---------------------------------------------------------------------------------------------------
+// Register-resident stage solver (MAXLEN = compile-time bound on the chain length, NCH = nq + 3 chains).
+// Same algebra as factor()/solve() above, but: the lane's chain lives in a register array through the
+// whole stage (sweeps fully unrolled, no index arithmetic, inactive rows masked instead of branched);
+// the shared-memory arrays are interleaved [l][chain] so every access is conflict-free at a constant
+// offset; only the (Phi', Psi) components are reduced over the warp (the Pi and v_b components exist on
+// the photon lanes only and are broadcast); the 4x4 border system is inverted once (Gauss-Jordan with
+// partial pivoting) so that each solve is a 4x4 mat-vec.
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr double RLc(int l) { return (double)l / (double)(2 * l + 1); }
+
+__device__ __forceinline__ double fast_rcp(double x) {   // x in [1, 1e30): float seed + 2 Newton steps (full double accuracy)
+  double y = (double)__frcp_rn(__double2float_rn(x));
+  double e = fma(-x, y, 1.0); y = fma(y, e, y);
+  e = fma(-x, y, 1.0); y = fma(y, e, y);
+  return y;
+}
+
+template <int MAXLEN>
+struct RegFactor {
+  double ibv[MAXLEN];
+  double beta0[4], beta1[4], beta2[4];
+  double inv[4][4];
+  double h, hk, hkap, vden, e4c, lo1, lo2;
+};
+
+__device__ __forceinline__ void inv4(const double (&Min)[4][4], double (&inv)[4][4]) {
+  double a[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) { a[i][j] = Min[i][j]; a[i][4 + j] = (i == j) ? 1.0 : 0.0; }
+#pragma unroll
+  for (int kx = 0; kx < 4; kx++) {
+    // partial pivoting: bring the largest |a[i][kx]|, i >= kx, to row kx (select-based swaps)
+#pragma unroll
+    for (int i = kx + 1; i < 4; i++) {
+      const bool sw = fabs(a[i][kx]) > fabs(a[kx][kx]);
+#pragma unroll
+      for (int j = kx; j < 8; j++) { const double t = a[kx][j]; a[kx][j] = sw ? a[i][j] : t; a[i][j] = sw ? t : a[i][j]; }
+    }
+    const double ip = 1.0 / a[kx][kx];
+#pragma unroll
+    for (int j = kx; j < 8; j++) a[kx][j] *= ip;
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (i != kx) {
+      const double m = a[i][kx];
+#pragma unroll
+      for (int j = kx + 1; j < 8; j++) a[i][j] -= m * a[kx][j];
+      a[i][kx] = 0.0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) inv[i][j] = a[i][4 + j];
+}
+
+template <int MAXLEN>
+__device__ __forceinline__ void factor_reg(const DevCosmo& c, const Lane& ln, const Bg& b, double h, RegFactor<MAXLEN>& f) {
+  const bool photon = (ln.kind == CH_T || ln.kind == CH_P);
+  f.h = h; f.hk = h * b.kappa * b.qe; f.hkap = h * b.kappa; f.vden = 1.0 / (1.0 + h);
+  f.e4c = -3.0 * h * b.taup * b.R;
+  const double dtau = photon ? -h * b.taup : 0.0;
+  const double btr = 1.0 + h * (double)ln.len / (b.H * b.eta) + dtau;
+  double ibn = 0.0, lo_next = 0.0;
+#pragma unroll
+  for (int l = MAXLEN - 1; l >= 3; l--) {
+    const bool act = l < ln.len, top = (l == ln.len - 1);
+    const double bd = top ? btr : 1.0 + dtau;
+    const double up = top ? 0.0 : f.hk * (1.0 - RLc(l));
+    const double lo = top ? -f.hk : -f.hk * RLc(l);
+    const double ibl = act ? fast_rcp(bd - (up * ibn) * lo_next) : 0.0;
+    f.ibv[l] = ibl; ibn = ibl; lo_next = act ? lo : 0.0;
+  }
+  const bool live = ln.kind != CH_IDLE;
+  const double up2 = f.hk * (1.0 - RLc(2)), up1 = f.hk * (1.0 - RLc(1)), up0 = f.hk;
+  const double lo2 = -f.hk * RLc(2), lo1 = -f.hk * RLc(1);
+  const double ib2 = live ? fast_rcp((1.0 + dtau) - (up2 * ibn) * lo_next) : 0.0;
+  const double m1 = up1 * ib2;
+  const double ib1 = live ? fast_rcp((1.0 + dtau) - m1 * lo2) : 0.0;
+  const double m0 = up0 * ib1;
+  const double ib0 = live ? fast_rcp((1.0 + (ln.kind == CH_P ? dtau : 0.0)) - m0 * lo1) : 0.0;
+  f.ibv[2] = ib2; f.ibv[1] = ib1; f.ibv[0] = ib0; f.lo1 = lo1; f.lo2 = lo2;
+  double C0[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0};
+  if (ln.kind == CH_M) { C0[0] = h * ln.df0; C1[1] = -f.hkap * (1.0 / 3.0) * b.eq * ln.df0; }
+  else if (ln.kind == CH_T) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); C1[3] = h * b.taup * (1.0 / 3.0); C2[2] = -h * b.taup * 0.1; }
+  else if (ln.kind == CH_P) { C0[2] = -h * b.taup * 0.5; C2[2] = -h * b.taup * 0.1; }
+  else if (ln.kind == CH_N) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const double V2 = C2[j], V1 = C1[j] - m1 * V2, V0 = C0[j] - m0 * V1;
+    f.beta0[j] = V0 * ib0;
+    f.beta1[j] = (V1 - lo1 * f.beta0[j]) * ib1;
+    f.beta2[j] = (V2 - lo2 * f.beta1[j]) * ib2;
+  }
+  // y-dependence of the Psi / Phi' / Pi sums.  Components (Pi, v_b) are non-zero on the Theta lane only (and Pi on
+  // the ThetaP lane), so only the (Phi', Psi) components need a warp reduction.
+  const int lT = ln.nq, lP = ln.nq + 1;
+  double sPsi[4], sPhi[4], sPi[4], t1[4];
+#pragma unroll
+  for (int j = 0; j < 2; j++) { sPsi[j] = warp_sum(b.wPsi * f.beta2[j]); sPhi[j] = warp_sum(b.wPhi * f.beta0[j]); }
+  const double wPsiT = shfl_d(b.wPsi, lT), wPhiT = shfl_d(b.wPhi, lT);
+#pragma unroll
+  for (int j = 2; j < 4; j++) { sPsi[j] = wPsiT * shfl_d(f.beta2[j], lT); sPhi[j] = wPhiT * shfl_d(f.beta0[j], lT); }
+#pragma unroll
+  for (int j = 0; j < 4; j++) { sPi[j] = shfl_d(f.beta2[j], lT); t1[j] = shfl_d(f.beta1[j], lT); }
+  sPi[2] += shfl_d(f.beta2[2] + f.beta0[2], lP);
+  const double Oc = c.s[BOLT_S_Omega_c] / b.a, Ob = c.s[BOLT_S_Omega_b] / b.a;
+  const double hk = f.hkap;
+  const double dPhi_y[4] = {h, 0, 0, 0};
+  const double dDel_y[4] = {-3.0 * h, -hk * hk * f.vden, 0, 0};
+  const double dDb_y[4] = {-3.0 * h, 0, 0, hk};
+  double M[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    M[0][j] = dPhi_y[j] + b.cPsi * sPsi[j] + (j == 1 ? 1.0 : 0.0);
+    M[1][j] = (j == 0 ? 1.0 : 0.0) - (j == 1 ? 1.0 : 0.0) + b.k2 * dPhi_y[j] - b.gPhi * (Oc * dDel_y[j] + Ob * dDb_y[j] + sPhi[j]);
+    M[2][j] = (j == 2 ? 1.0 : 0.0) - sPi[j];
+    M[3][j] = (j == 3 ? (1.0 + h - h * b.taup * b.R) : 0.0) + hk * ((j == 1 ? 1.0 : 0.0) + b.csb2 * dDb_y[j]) + f.e4c * t1[j];
+  }
+  inv4(M, f.inv);
+}
+
+// Solve W U = r for the lane's chain in rr[] (registers, overwritten by U) and the 5 scalars in r5[] (every lane
+// holds the same copy).
+template <int MAXLEN>
+__device__ __forceinline__ void solve_reg(const DevCosmo& c, const Lane& ln, const Bg& b, const RegFactor<MAXLEN>& f,
+                                          double (&rr)[MAXLEN], double (&r5)[5]) {
+  double ibn = 0.0, rn = 0.0;
+#pragma unroll
+  for (int l = MAXLEN - 1; l >= 3; l--) {
+    const bool top = (l == ln.len - 1);
+    const double up = top ? 0.0 : f.hk * (1.0 - RLc(l));
+    const double v = rr[l] - (up * ibn) * rn;
+    rr[l] = v; rn = v; ibn = f.ibv[l];
+  }
+  const double r2 = rr[2] - (f.hk * (1.0 - RLc(2)) * ibn) * rn;
+  const double r1 = rr[1] - (f.hk * (1.0 - RLc(1)) * f.ibv[2]) * r2;
+  const double r0 = rr[0] - (f.hk * f.ibv[1]) * r1;
+  const double a0 = r0 * f.ibv[0], a1 = (r1 - f.lo1 * a0) * f.ibv[1], a2 = (r2 - f.lo2 * a1) * f.ibv[2];
+  const int lT = ln.nq, lP = ln.nq + 1;
+  const double sPsi = warp_sum(b.wPsi * a2);
+  const double sPhi = warp_sum(b.wPhi * a0);
+  const double sPi = shfl_d(a2, lT) + shfl_d(a2 + a0, lP);
+  const double t1 = shfl_d(a1, lT);
+  const double rPhi = r5[0], rdel = r5[1], rv = r5[2], rdb = r5[3], rvb = r5[4];
+  const double Oc = c.s[BOLT_S_Omega_c] / b.a, Ob = c.s[BOLT_S_Omega_b] / b.a;
+  const double hk = f.hkap, h = f.h;
+  const double vc = rv * f.vden, dc = rdel + hk * vc;
+  double rhs[4], y[4];
+  rhs[0] = -(rPhi + b.cPsi * sPsi);
+  rhs[1] = -(b.k2 * rPhi - b.gPhi * (Oc * dc + Ob * rdb + sPhi));
+  rhs[2] = sPi;
+  rhs[3] = -(hk * b.csb2 * rdb + f.e4c * t1 - rvb);
+#pragma unroll
+  for (int i = 0; i < 4; i++) y[i] = f.inv[i][0] * rhs[0] + f.inv[i][1] * rhs[1] + f.inv[i][2] * rhs[2] + f.inv[i][3] * rhs[3];
+  r5[0] = rPhi + h * y[0];
+  const double v = vc - hk * f.vden * y[1];
+  r5[1] = rdel + hk * v - 3.0 * h * y[0];
+  r5[2] = v;
+  r5[3] = rdb - 3.0 * h * y[0] + hk * y[3];
+  r5[4] = y[3];
+  double U0 = a0, U1 = a1, U2 = a2;
+#pragma unroll
+  for (int j = 0; j < 4; j++) { U0 += f.beta0[j] * y[j]; U1 += f.beta1[j] * y[j]; U2 += f.beta2[j] * y[j]; }
+  rr[0] = U0; rr[1] = U1; rr[2] = U2;
+  double Up = U2;
+#pragma unroll
+  for (int l = 3; l < MAXLEN; l++) {
+    const bool top = (l == ln.len - 1);
+    const double lo = top ? -f.hk : -f.hk * RLc(l);
+    const double U = (rr[l] - lo * Up) * f.ibv[l];
+    rr[l] = U; Up = U;
+  }
+}
+
+// Chain ownership of a lane for cosmology c.  MAXLEN == 0: generic layout = the reference's unpack order.
+// MAXLEN > 0: interleaved layout [l][chain] (+5 scalars after MAXLEN*NCH) for the register-resident solver.
+template <int MAXLEN, int NQ>
+__device__ __forceinline__ void lane_setup(const DevCosmo& c, const SolveParams& p, Lane& ln) {
+  ln.lane = threadIdx.x; ln.nq = c.nq; ln.L = p.L; ln.n = p.n;
+  ln.riS = 2 * (p.L + 1) + (p.Lnu + 1) + (p.Lm + 1) * c.nq;
   ln.maxlen = max(p.L, max(p.Lnu, p.Lm)) + 1;
   ln.q = 0; ln.df0 = 0; ln.wq = 0;
-  if (ln.lane < c.nq) { ln.kind = CH_M; ln.base = 2 * (p.L + 1) + (p.Lnu + 1) + ln.lane; ln.stride = c.nq; ln.len = p.Lm + 1;
+  if (ln.lane < c.nq) { ln.kind = CH_M; ln.rbase = 2 * (p.L + 1) + (p.Lnu + 1) + ln.lane; ln.rstride = c.nq; ln.len = p.Lm + 1;
                         ln.q = c.q[ln.lane]; ln.df0 = c.df0[ln.lane]; ln.wq = c.wq[ln.lane]; }
-  else if (ln.lane == c.nq) { ln.kind = CH_T; ln.base = 0; ln.stride = 1; ln.len = p.L + 1; }
-  else if (ln.lane == c.nq + 1) { ln.kind = CH_P; ln.base = p.L + 1; ln.stride = 1; ln.len = p.L + 1; }
-  else if (ln.lane == c.nq + 2) { ln.kind = CH_N; ln.base = 2 * (p.L + 1); ln.stride = 1; ln.len = p.Lnu + 1; }
-  else { ln.kind = CH_IDLE; ln.base = 0; ln.stride = 0; ln.len = 0; }
+  else if (ln.lane == c.nq) { ln.kind = CH_T; ln.rbase = 0; ln.rstride = 1; ln.len = p.L + 1; }
+  else if (ln.lane == c.nq + 1) { ln.kind = CH_P; ln.rbase = p.L + 1; ln.rstride = 1; ln.len = p.L + 1; }
+  else if (ln.lane == c.nq + 2) { ln.kind = CH_N; ln.rbase = 2 * (p.L + 1); ln.rstride = 1; ln.len = p.Lnu + 1; }
+  else { ln.kind = CH_IDLE; ln.rbase = 0; ln.rstride = 0; ln.len = 0; }
+  if constexpr (MAXLEN > 0) { ln.base = (ln.kind == CH_IDLE) ? 0 : ln.lane; ln.stride = (ln.kind == CH_IDLE) ? 0 : NQ + 3; ln.iS = MAXLEN * (NQ + 3); }
+  else { ln.base = ln.rbase; ln.stride = ln.rstride; ln.iS = ln.riS; }
+}
 
-  const double x_begin = c.x0, x_end = 0.0;
+// Shared-memory doubles per warp.
+template <int MAXLEN, int NQ>
+__host__ __device__ constexpr int k1_array_len(int n) { return MAXLEN > 0 ? MAXLEN * (NQ + 3) + 8 : n; }
+template <int MAXLEN, int NQ>
+__host__ __device__ constexpr int k1_num_arrays() { return MAXLEN > 0 ? 7 : 9; }
+
+template <int MAXLEN, int NQ>
+__global__ void __launch_bounds__(32) hierarchy_kernel_t(SolveParams p) {
+  extern __shared__ double sm[];
+  constexpr int NCH = NQ + 3;
+  const int n = p.n;
+  const int na = k1_array_len<MAXLEN, NQ>(n);
+  Lane ln;
   const bool fixed = (p.mode == BOLT_MODE_FIXED);
   const double reltol = p.reltol, abstol = p.abstol;
 
   while (true) {
     int w = 0;
-    if (ln.lane == 0) w = atomicAdd(p.counter, 1);
+    if (threadIdx.x == 0) w = atomicAdd(p.counter, 1);
     w = __shfl_sync(FULL, w, 0);
     if (w >= p.nk) break;
     const int ik = p.order[w];
+    const DevCosmo& c = *p.cos_list[ik / p.nk_per];
+    lane_setup<MAXLEN, NQ>(c, p, ln);
     ln.k = p.k[ik];
+    const double x_begin = c.x0, x_end = 0.0;
 
-    // Array slots.  u/u_{n+1} and z1/z6 swap roles on every accepted step (no copies): physical slot 0/2
-    // hold u and u_{n+1} (alias of the z2 slot, which is free once the error estimate is formed), slots
-    // 1/6 hold z1 and z6.  z3..z5 are fixed.
+    // Array slots.  u/u_{n+1} and z1/z6 swap roles on every accepted step (no copies): physical slots 0/2 hold u and
+    // u_{n+1} (alias of the z2 slot, free once the error estimate is formed), slots 1/6 hold z1 and z6; z3..z5 fixed.
     bool flipU = false, flipZ = false;
-    double* const Z2 = sm + (size_t)3 * n;
-    double* const Z3 = sm + (size_t)4 * n;
-    double* const Z4 = sm + (size_t)5 * n;
-    double* r = sm + (size_t)7 * n;
-    double* ib = sm + (size_t)8 * n;
-#define SLOT_U  (sm + (flipU ? (size_t)2 * n : (size_t)0))
-#define SLOT_Z1 (sm + (flipU ? (size_t)0 : (size_t)2 * n))
-#define SLOT_Z0 (sm + (flipZ ? (size_t)6 * n : (size_t)n))
-#define SLOT_Z5 (sm + (flipZ ? (size_t)n : (size_t)6 * n))
+    double* const Z2 = sm + (size_t)3 * na;
+    double* const Z3 = sm + (size_t)4 * na;
+    double* const Z4 = sm + (size_t)5 * na;
+    double* r = (MAXLEN > 0) ? Z2 : sm + (size_t)7 * na;          // scratch (generic: work vector of the solver)
+    double* ib = (MAXLEN > 0) ? nullptr : sm + (size_t)8 * na;    // generic: inverse pivots
+#define SLOT_U  (sm + (flipU ? (size_t)2 * na : (size_t)0))
+#define SLOT_Z1 (sm + (flipU ? (size_t)0 : (size_t)2 * na))
+#define SLOT_Z0 (sm + (flipZ ? (size_t)6 * na : (size_t)na))
+#define SLOT_Z5 (sm + (flipZ ? (size_t)na : (size_t)6 * na))
     double* U = SLOT_U; double* Z0 = SLOT_Z0; double* Z1 = SLOT_Z1; double* Z5 = SLOT_Z5;
+    if constexpr (MAXLEN > 0) {   // zero-coefficient terms are still loaded by the branch-free stage assembly
+      for (int i = ln.lane; i < 7 * na; i += 32) sm[i] = 0.0;
+      __syncwarp();
+    }
 
     Bg b;
     eval_bg(c, ln, x_begin, b);
     initial_conditions(c, ln, b, U);
-    rhs_full(c, ln, b, U, Z5);          // f(u0) in Z[5] (plays the role of z6/dt of a previous step)
+    rhs_full(c, ln, b, U, Z5);          // f(u0) in the z6 slot (plays the role of z6/dt of a previous step)
     bool rsa_flag = (ln.k * b.eta > 240.0) && (-b.taup * b.H / b.eta > 100.0);
 
     int ix = 0;
@@ -627,7 +827,7 @@ __global__ void __launch_bounds__(32) hierarchy_kernel(SolveParams p) {
       const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(dm)) / 5.0);
       dt = fmin(100.0 * dt0, dt1);
     }
-    // Z[0] <- f(u0): true z1 = s1 * Z[0] with s1 = dt
+    // z1 slot <- f(u0): true z1 = s1 * Z0 with s1 = dt
     flipZ = !flipZ; Z0 = SLOT_Z0; Z5 = SLOT_Z5;
     double s1 = dt;
 
@@ -646,46 +846,134 @@ __global__ void __launch_bounds__(32) hierarchy_kernel(SolveParams p) {
       }
       if (nsteps + nreject >= max_steps) { status = BOLT_K_MAXSTEPS; break; }
 
-      Factor f;
       Bg bs;
-      for (int s = 1; s < 6; s++) {
-        const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
-        const double* z0 = Z0; const double* z1p = Z1; const double* z2p = Z2; const double* z3p = Z3; const double* z4p = Z4;
-        auto rhs_of = [&](int idx) {
-          double v = U[idx] + a0 * z0[idx];
-          if (s > 1) v += a1 * z1p[idx];
-          if (s > 2) v += a2 * z2p[idx];
-          if (s > 3) v += a3 * z3p[idx];
-          if (s > 4) v += a4 * z4p[idx];
-          return v;
-        };
-        for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; r[idx] = rhs_of(idx); }
-        if (ln.lane < 5) { const int idx = ln.iS + ln.lane; r[idx] = rhs_of(idx); }
-        __syncwarp();
-        eval_bg(c, ln, x + KC_C[s] * dt, bs);
-        rsa_flag |= (ln.k * bs.eta > 240.0) && (-bs.taup * bs.H / bs.eta > 100.0);
-        factor(c, ln, bs, KC_GAMMA * dt, ib, f);
-        double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
-        solve(c, ln, bs, f, ib, r, zout, rhs_of);
-      }
-      // error estimate err = sum (b - bhat)_j z_j, and u_{n+1} = u_n + sum b_j z_j (= U_6 up to rounding).
-      // u_{n+1} goes to the Z[1] slot, which is free once err is formed.
-      {
-        const double e0 = KC_E[0] * s1, b0 = KC_A[5][0] * s1;
-        auto pass = [&](int idx) {
-          const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
-          r[idx] = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
-          Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
-        };
-        for (int l = 0; l < ln.len; l++) pass(ln.base + l * ln.stride);
-        if (ln.lane < 5) pass(ln.iS + ln.lane);
-        __syncwarp();
-      }
       bool accept = true; double EEst = 0.0, q11 = 0.0;
+      if constexpr (MAXLEN > 0) {
+        // ---------------- register-resident stages ----------------
+        RegFactor<MAXLEN> f;
+        double rr[MAXLEN], rh[MAXLEN], r5[5], rh5[5];
+        const int lo_ = ln.lane;   // lane offset inside a row of the interleaved layout
+        for (int s = 1; s < 6; s++) {
+          // branch-free assembly: coefficients of stages >= s are zero
+          const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
+#pragma unroll
+          for (int l = 0; l < MAXLEN; l++) {
+            double v = 0.0;
+            if (l < ln.len) {
+              const int idx = lo_ + l * NCH;
+              v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
+            }
+            rr[l] = v; rh[l] = v;
+          }
+#pragma unroll
+          for (int j = 0; j < 5; j++) {
+            const int idx = ln.iS + j;
+            const double v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
+            r5[j] = v; rh5[j] = v;
+          }
+          eval_bg(c, ln, x + KC_C[s] * dt, bs);
+          rsa_flag |= (ln.k * bs.eta > 240.0) && (-bs.taup * bs.H / bs.eta > 100.0);
+          factor_reg<MAXLEN>(c, ln, bs, KC_GAMMA * dt, f);
+          solve_reg<MAXLEN>(c, ln, bs, f, rr, r5);
+          double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
+          __syncwarp();
+#pragma unroll
+          for (int l = 0; l < MAXLEN; l++) if (l < ln.len) zout[lo_ + l * NCH] = (rr[l] - rh[l]) * (1.0 / KC_GAMMA);
+          if (ln.lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 5; j++) zout[ln.iS + j] = (r5[j] - rh5[j]) * (1.0 / KC_GAMMA);
+          }
+          __syncwarp();
+        }
+        // error estimate and u_{n+1} = u_n + sum b_j z_j (into the z2 slot)
+        {
+          const double e0 = KC_E[0] * s1, b0 = KC_A[5][0] * s1;
+#pragma unroll
+          for (int l = 0; l < MAXLEN; l++) {
+            double e = 0.0;
+            if (l < ln.len) {
+              const int idx = lo_ + l * NCH;
+              const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
+              e = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
+              Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
+            }
+            rr[l] = e;
+          }
+          double un5[5];
+#pragma unroll
+          for (int j = 0; j < 5; j++) {
+            const int idx = ln.iS + j;
+            const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
+            r5[j] = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
+            un5[j] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
+          }
+          __syncwarp();
+          if (ln.lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 5; j++) Z1[ln.iS + j] = un5[j];
+          }
+          __syncwarp();
+        }
+        if (!fixed) {
+          solve_reg<MAXLEN>(c, ln, bs, f, rr, r5);      // smooth_est: W^{-1} err with the last stage's W
+          double ssum = 0.0;
+#pragma unroll
+          for (int l = 0; l < MAXLEN; l++) if (l < ln.len) {
+            const int idx = lo_ + l * NCH;
+            const double sc = abstol + reltol * fmax(fabs(U[idx]), fabs(Z1[idx]));
+            const double q = rr[l] / sc; ssum += q * q;
+          }
+          if (ln.lane < 5) {
+            double e = r5[0]; e = (ln.lane == 1) ? r5[1] : e; e = (ln.lane == 2) ? r5[2] : e; e = (ln.lane == 3) ? r5[3] : e; e = (ln.lane == 4) ? r5[4] : e;
+            const int idx = ln.iS + ln.lane;
+            const double sc = abstol + reltol * fmax(fabs(U[idx]), fabs(Z1[idx]));
+            const double q = e / sc; ssum += q * q;
+          }
+          EEst = sqrt(warp_sum(ssum) / n);
+        }
+      } else {
+        // ---------------- generic stages (runtime chain lengths, work vectors in shared memory) ----------------
+        Factor f;
+        for (int s = 1; s < 6; s++) {
+          const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
+          const double* z0 = Z0; const double* z1p = Z1; const double* z2p = Z2; const double* z3p = Z3; const double* z4p = Z4;
+          auto rhs_of = [&](int idx) {
+            double v = U[idx] + a0 * z0[idx];
+            if (s > 1) v += a1 * z1p[idx];
+            if (s > 2) v += a2 * z2p[idx];
+            if (s > 3) v += a3 * z3p[idx];
+            if (s > 4) v += a4 * z4p[idx];
+            return v;
+          };
+          for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; r[idx] = rhs_of(idx); }
+          if (ln.lane < 5) { const int idx = ln.iS + ln.lane; r[idx] = rhs_of(idx); }
+          __syncwarp();
+          eval_bg(c, ln, x + KC_C[s] * dt, bs);
+          rsa_flag |= (ln.k * bs.eta > 240.0) && (-bs.taup * bs.H / bs.eta > 100.0);
+          factor(c, ln, bs, KC_GAMMA * dt, ib, f);
+          double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
+          solve(c, ln, bs, f, ib, r, zout, rhs_of);
+        }
+        // error estimate err = sum (b - bhat)_j z_j, and u_{n+1} = u_n + sum b_j z_j (= U_6 up to rounding).
+        // u_{n+1} goes to the z2 slot, which is free once err is formed.
+        {
+          const double e0 = KC_E[0] * s1, b0 = KC_A[5][0] * s1;
+          auto pass = [&](int idx) {
+            const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
+            r[idx] = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
+            Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
+          };
+          for (int l = 0; l < ln.len; l++) pass(ln.base + l * ln.stride);
+          if (ln.lane < 5) pass(ln.iS + ln.lane);
+          __syncwarp();
+        }
+        if (!fixed) {
+          auto none = [&](int) { return 0.0; };
+          solve(c, ln, bs, f, ib, r, (double*)nullptr, none);      // smooth_est: W^{-1} err with the last stage's W
+          EEst = sqrt(sumsq_scaled(r, U, Z1) / n);
+        }
+      }
       if (!fixed) {
-        auto none = [&](int) { return 0.0; };
-        solve(c, ln, bs, f, ib, r, (double*)nullptr, none);      // smooth_est: W^{-1} err with the last stage's W
-        EEst = sqrt(sumsq_scaled(r, U, Z1) / n);
         if (!isfinite(EEst)) { status = BOLT_K_NONFINITE; break; }
         // Controller input floored at 1e-6: below that the estimate is rounding noise of the stiff start-up phase and
         // would make the step sequence implementation-dependent (DESIGN.md "controller"); acceptance uses the raw value.
@@ -730,8 +1018,8 @@ __global__ void __launch_bounds__(32) hierarchy_kernel(SolveParams p) {
     if (rsa_flag && status == BOLT_K_OK) status = BOLT_K_RSA_TRIGGERED;
     if (p.u_final) {
       double* out = p.u_final + (size_t)ik * n;
-      for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; out[idx] = U[idx]; }
-      if (ln.lane < 5) out[ln.iS + ln.lane] = U[ln.iS + ln.lane];
+      for (int l = 0; l < ln.len; l++) out[ln.rbase + l * ln.rstride] = U[ln.base + l * ln.stride];
+      if (ln.lane < 5) out[ln.riS + ln.lane] = U[ln.iS + ln.lane];
     }
     if (ln.lane == 0) {
       if (p.status) p.status[ik] = status;
