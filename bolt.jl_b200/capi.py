@@ -10,7 +10,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbolt_cuda.so")
+LIB_PATH = os.environ.get("BOLT_CUDA_LIB", os.path.join(_HERE, "csrc", "libbolt_cuda.so"))
 _LIB = None
 
 EXPORTS = ["bolt_abi_version", "bolt_init", "bolt_finalize", "bolt_last_error", "bolt_last_timing",

@@ -94,10 +94,10 @@ int check_opts(bolt_ctx* ctx, const bolt_cosmo* c, const bolt_opts* o) {
   return BOLT_OK;
 }
 
-template <int MAXLEN, int NQ>
+template <class TR>
 int launch_k1(bolt_ctx* ctx, const SolveParams& p) {
-  auto kern = hierarchy_kernel_t<MAXLEN, NQ>;
-  const size_t smem = (size_t)k1_num_arrays<MAXLEN, NQ>() * k1_array_len<MAXLEN, NQ>(p.n) * sizeof(double);
+  auto kern = hierarchy_kernel_t<TR>;
+  const size_t smem = (size_t)k1_num_arrays<TR>() * k1_array_len<TR>(p.n) * sizeof(double);
   CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int occ = 0;
@@ -127,10 +127,12 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   p.S_T = d_ST; p.S_P = d_SP; p.u_hist = d_hist; p.u_final = d_final;
   p.status = d_status; p.nsteps = d_nsteps; p.nreject = d_nreject; p.counter = ctx->d_counter;
   p.dbg = ctx->d_dbg; p.dbg_cap = ctx->d_dbg ? DBG_CAP : 0;
-  const int maxlen = std::max(p.L, std::max(p.Lnu, p.Lm)) + 1;
   const bool force_generic = getenv("BOLT_K1_GENERIC") != nullptr;     // development switch
-  if (!force_generic && nq == 15 && maxlen <= 11) return launch_k1<11, 15>(ctx, p);   // source_grid defaults (l_gamma <= 10)
-  return launch_k1<0, 0>(ctx, p);                                                      // any truncation (plin: 50, 50, 20)
+  if (!force_generic && nq == 15 && p.Lnu == 8 && p.Lm == 10) {          // source_grid's truncations (src/spectra.jl:11)
+    if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15>>(ctx, p);         // l_gamma = 8: the reference default
+    if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15>>(ctx, p);       // l_gamma = 10: BASELINE config 1
+  }
+  return launch_k1<Trunc<0, 0, 0, 0>>(ctx, p);                            // any truncation (plin: 50, 50, 20)
 }
 int launch_hierarchy(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, const int* d_order, int nk, const bolt_opts* o,
                      double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status, long long* d_nsteps,

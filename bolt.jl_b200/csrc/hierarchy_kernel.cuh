@@ -540,94 +540,153 @@ __device__ __forceinline__ void sample_sources(const DevCosmo& c, const Lane& ln
 // Shared memory per warp: 9 arrays of n doubles: u, z1..z6, work r, inverse pivots ib.
 // ---------------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------------
-// Register-resident stage solver (MAXLEN = compile-time bound on the chain length, NCH = nq + 3 chains).
-// Same algebra as factor()/solve() above, but: the lane's chain lives in a register array through the
-// whole stage (sweeps fully unrolled, no index arithmetic, inactive rows masked instead of branched);
-// the shared-memory arrays are interleaved [l][chain] so every access is conflict-free at a constant
-// offset; only the (Phi', Psi) components are reduced over the warp (the Pi and v_b components exist on
-// the photon lanes only and are broadcast); the 4x4 border system is inverted once (Gauss-Jordan with
-// partial pivoting) so that each solve is a 4x4 mat-vec.
+// Register-resident stage solver, specialised at compile time on the truncations TR = Trunc<l_gamma, l_nu, l_mnu, nq>.
+// Same algebra as factor()/solve() above, but: the lane's chain lives in a register array through the whole
+// stage (sweeps fully unrolled, no index arithmetic; "is this the truncation row of my chain" folds to a
+// compile-time constant except at the two or three rows where some chain ends); the shared-memory arrays are
+// interleaved [l][chain] so every access is conflict-free at a constant offset; only the (Phi', Psi)
+// components are reduced over the warp (the Pi and v_b components live on the photon lanes and are broadcast);
+// the 4x4 border system is kept as a matrix and solved per right-hand side by Gaussian elimination with
+// partial pivoting on the augmented 4x5 system (cheaper than a stored factorisation with permutation logic).
 // ---------------------------------------------------------------------------------------------------
+template <int LG_, int LNU_, int LMNU_, int NQ_>
+struct Trunc {
+  static constexpr int LG = LG_, LNU = LNU_, LMNU = LMNU_, NQ = NQ_;
+  static constexpr int MAXL = (LG_ > LNU_ ? (LG_ > LMNU_ ? LG_ : LMNU_) : (LNU_ > LMNU_ ? LNU_ : LMNU_));
+  static constexpr int MAXLEN = (NQ_ > 0) ? MAXL + 1 : 0;     // 0 = generic (runtime) kernel
+  static constexpr int NCH = NQ_ + 3;
+  // row l is the truncation row / an existing row of the lane's chain
+  static __device__ __forceinline__ bool top(int kind, int l) {
+    return (l == LG_ && (kind == CH_T || kind == CH_P)) || (l == LNU_ && kind == CH_N) || (l == LMNU_ && kind == CH_M);
+  }
+  static __device__ __forceinline__ bool act(int kind, int l) {
+    return (l <= LG_ && (kind == CH_T || kind == CH_P)) || (l <= LNU_ && kind == CH_N) || (l <= LMNU_ && kind == CH_M);
+  }
+};
+
 __host__ __device__ constexpr double RLc(int l) { return (double)l / (double)(2 * l + 1); }
 
-__device__ __forceinline__ double fast_rcp(double x) {   // x in [1, 1e30): float seed + 2 Newton steps (full double accuracy)
-  double y = (double)__frcp_rn(__double2float_rn(x));
+// 1/x for normal x: MUFU.RCP64H seed (~20 bits) + 2 Newton steps (full double accuracy; not correctly rounded)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = fma(-x, y, 1.0); y = fma(y, e, y);
   e = fma(-x, y, 1.0); y = fma(y, e, y);
   return y;
 }
 
-template <int MAXLEN>
+// Per-mode constants of the fast background evaluation
+struct ModeConst {
+  double k, k2_3, c12, H02h, R0, Oc, Ob, mnu;      // k, k^2/3, 12 H0^2/k^2, H0^2/2, 4 Om_r/(3 Om_b), Om_c, Om_b, sum m_nu
+  double q2, iq, wPhi0, wPsi0;                       // lane: q^2, 1/q, weight prefactors (see eval_bg_fast)
+};
+__device__ __forceinline__ void mode_const(const DevCosmo& c, const Lane& ln, ModeConst& mc) {
+  const double H0 = c.s[BOLT_S_H0], rho_crit = c.s[BOLT_S_rho_crit], Om_r = c.s[BOLT_S_Omega_r];
+  mc.k = ln.k; mc.k2_3 = ln.k * ln.k / 3.0; mc.c12 = 12.0 * H0 * H0 / (ln.k * ln.k); mc.H02h = 0.5 * H0 * H0;
+  mc.R0 = 4.0 * Om_r / (3.0 * c.s[BOLT_S_Omega_b]); mc.Oc = c.s[BOLT_S_Omega_c]; mc.Ob = c.s[BOLT_S_Omega_b];
+  mc.mnu = c.s[BOLT_S_Sum_m_nu];
+  mc.q2 = ln.q * ln.q; mc.iq = (ln.kind == CH_M) ? 1.0 / ln.q : 1.0;
+  mc.wPhi0 = 0.0; mc.wPsi0 = 0.0;
+  if (ln.kind == CH_M) { mc.wPhi0 = ln.wq / rho_crit; mc.wPsi0 = ln.wq * mc.q2 / rho_crit * 0.25; }
+  else if (ln.kind == CH_T) { mc.wPhi0 = 4.0 * Om_r; mc.wPsi0 = Om_r; }
+  else if (ln.kind == CH_N) { mc.wPhi0 = 4.0 * c.Omega_nu; mc.wPsi0 = c.Omega_nu; }
+}
+
+// Stage-time background: same quantities as eval_bg with the divisions hoisted (4 reciprocals, 1 exp, 1 sqrt).
+struct BgS {
+  double H, eta, taup, csb2, a;
+  double kappa, qe, eq, wPsi, wPhi, cPsi, gPhi, k2, R, Oc_a, Ob_a, iHeta;
+};
+__device__ __forceinline__ void eval_bg_fast(const DevCosmo& c, const Lane& ln, const ModeConst& mc, double x, BgS& b) {
+  const int which[4] = {BOLT_T_H, BOLT_T_eta, BOLT_T_taup, BOLT_T_csb2};
+  double v = 0.0;
+  if (ln.lane < 4) v = spline_eval(c.tab[which[ln.lane]], c.n_x, c.x0, c.dx, x);
+  b.H = shfl_d(v, 0); b.eta = shfl_d(v, 1); b.taup = shfl_d(v, 2); b.csb2 = shfl_d(v, 3);
+  b.a = exp(x);
+  const double ia = fast_rcp(b.a), ia2 = ia * ia, iH = fast_rcp(b.H), iH2 = iH * iH;
+  b.kappa = mc.k * iH; b.R = mc.R0 * ia; b.cPsi = mc.c12 * ia2; b.gPhi = mc.H02h * iH2; b.k2 = mc.k2_3 * iH2;
+  b.Oc_a = mc.Oc * ia; b.Ob_a = mc.Ob * ia; b.iHeta = iH * fast_rcp(b.eta);
+  b.qe = 1.0; b.eq = 1.0;
+  if (ln.kind == CH_M) {
+    const double am = b.a * mc.mnu;
+    const double eps = sqrt(mc.q2 + am * am), ieps = fast_rcp(eps);
+    b.qe = ln.q * ieps; b.eq = eps * mc.iq;
+    b.wPhi = mc.wPhi0 * eps * ia2; b.wPsi = mc.wPsi0 * ieps;
+  } else { b.wPhi = mc.wPhi0 * ia2; b.wPsi = mc.wPsi0; }
+}
+
+template <class TR>
 struct RegFactor {
-  double ibv[MAXLEN];
+  double ibv[TR::MAXLEN > 0 ? TR::MAXLEN : 1];
   double beta0[4], beta1[4], beta2[4];
-  double inv[4][4];
+  double M[4][4];
   double h, hk, hkap, vden, e4c, lo1, lo2;
 };
 
-__device__ __forceinline__ void inv4(const double (&Min)[4][4], double (&inv)[4][4]) {
-  double a[4][8];
+// Solve M y = rhs by Gaussian elimination with partial pivoting on the augmented system (registers, select-based swaps).
+__device__ __forceinline__ void ge4(const double (&Min)[4][4], const double (&rhs)[4], double (&y)[4]) {
+  double a[4][5];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 4; i++) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) { a[i][j] = Min[i][j]; a[i][4 + j] = (i == j) ? 1.0 : 0.0; }
+    for (int j = 0; j < 4; j++) a[i][j] = Min[i][j];
+    a[i][4] = rhs[i];
+  }
 #pragma unroll
-  for (int kx = 0; kx < 4; kx++) {
-    // partial pivoting: bring the largest |a[i][kx]|, i >= kx, to row kx (select-based swaps)
+  for (int kx = 0; kx < 3; kx++) {
 #pragma unroll
     for (int i = kx + 1; i < 4; i++) {
       const bool sw = fabs(a[i][kx]) > fabs(a[kx][kx]);
 #pragma unroll
-      for (int j = kx; j < 8; j++) { const double t = a[kx][j]; a[kx][j] = sw ? a[i][j] : t; a[i][j] = sw ? t : a[i][j]; }
+      for (int j = kx; j < 5; j++) { const double t = a[kx][j]; a[kx][j] = sw ? a[i][j] : t; a[i][j] = sw ? t : a[i][j]; }
     }
-    const double ip = 1.0 / a[kx][kx];
+    const double ip = fast_rcp(a[kx][kx]);
 #pragma unroll
-    for (int j = kx; j < 8; j++) a[kx][j] *= ip;
+    for (int i = kx + 1; i < 4; i++) {
+      const double m = a[i][kx] * ip;
 #pragma unroll
-    for (int i = 0; i < 4; i++) if (i != kx) {
-      const double m = a[i][kx];
-#pragma unroll
-      for (int j = kx + 1; j < 8; j++) a[i][j] -= m * a[kx][j];
-      a[i][kx] = 0.0;
+      for (int j = kx + 1; j < 5; j++) a[i][j] -= m * a[kx][j];
     }
   }
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) inv[i][j] = a[i][4 + j];
+  y[3] = a[3][4] * fast_rcp(a[3][3]);
+  y[2] = (a[2][4] - a[2][3] * y[3]) * fast_rcp(a[2][2]);
+  y[1] = (a[1][4] - a[1][2] * y[2] - a[1][3] * y[3]) * fast_rcp(a[1][1]);
+  y[0] = (a[0][4] - a[0][1] * y[1] - a[0][2] * y[2] - a[0][3] * y[3]) * fast_rcp(a[0][0]);
 }
 
-template <int MAXLEN>
-__device__ __forceinline__ void factor_reg(const DevCosmo& c, const Lane& ln, const Bg& b, double h, RegFactor<MAXLEN>& f) {
-  const bool photon = (ln.kind == CH_T || ln.kind == CH_P);
-  f.h = h; f.hk = h * b.kappa * b.qe; f.hkap = h * b.kappa; f.vden = 1.0 / (1.0 + h);
+template <class TR>
+__device__ __forceinline__ void factor_reg(const Lane& ln, const BgS& b, double h, RegFactor<TR>& f) {
+  constexpr int MAXLEN = TR::MAXLEN;
+  const int kind = ln.kind;
+  const bool photon = (kind == CH_T || kind == CH_P);
+  f.h = h; f.hk = h * b.kappa * b.qe; f.hkap = h * b.kappa; f.vden = fast_rcp(1.0 + h);
   f.e4c = -3.0 * h * b.taup * b.R;
   const double dtau = photon ? -h * b.taup : 0.0;
-  const double btr = 1.0 + h * (double)ln.len / (b.H * b.eta) + dtau;
+  const double btr = 1.0 + h * (double)ln.len * b.iHeta + dtau;
   double ibn = 0.0, lo_next = 0.0;
 #pragma unroll
   for (int l = MAXLEN - 1; l >= 3; l--) {
-    const bool act = l < ln.len, top = (l == ln.len - 1);
+    const bool act = TR::act(kind, l), top = TR::top(kind, l);
     const double bd = top ? btr : 1.0 + dtau;
     const double up = top ? 0.0 : f.hk * (1.0 - RLc(l));
     const double lo = top ? -f.hk : -f.hk * RLc(l);
     const double ibl = act ? fast_rcp(bd - (up * ibn) * lo_next) : 0.0;
     f.ibv[l] = ibl; ibn = ibl; lo_next = act ? lo : 0.0;
   }
-  const bool live = ln.kind != CH_IDLE;
+  const bool live = kind != CH_IDLE;
   const double up2 = f.hk * (1.0 - RLc(2)), up1 = f.hk * (1.0 - RLc(1)), up0 = f.hk;
   const double lo2 = -f.hk * RLc(2), lo1 = -f.hk * RLc(1);
   const double ib2 = live ? fast_rcp((1.0 + dtau) - (up2 * ibn) * lo_next) : 0.0;
   const double m1 = up1 * ib2;
   const double ib1 = live ? fast_rcp((1.0 + dtau) - m1 * lo2) : 0.0;
   const double m0 = up0 * ib1;
-  const double ib0 = live ? fast_rcp((1.0 + (ln.kind == CH_P ? dtau : 0.0)) - m0 * lo1) : 0.0;
+  const double ib0 = live ? fast_rcp((1.0 + (kind == CH_P ? dtau : 0.0)) - m0 * lo1) : 0.0;
   f.ibv[2] = ib2; f.ibv[1] = ib1; f.ibv[0] = ib0; f.lo1 = lo1; f.lo2 = lo2;
   double C0[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0};
-  if (ln.kind == CH_M) { C0[0] = h * ln.df0; C1[1] = -f.hkap * (1.0 / 3.0) * b.eq * ln.df0; }
-  else if (ln.kind == CH_T) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); C1[3] = h * b.taup * (1.0 / 3.0); C2[2] = -h * b.taup * 0.1; }
-  else if (ln.kind == CH_P) { C0[2] = -h * b.taup * 0.5; C2[2] = -h * b.taup * 0.1; }
-  else if (ln.kind == CH_N) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); }
+  if (kind == CH_M) { C0[0] = h * ln.df0; C1[1] = -f.hkap * (1.0 / 3.0) * b.eq * ln.df0; }
+  else if (kind == CH_T) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); C1[3] = h * b.taup * (1.0 / 3.0); C2[2] = -h * b.taup * 0.1; }
+  else if (kind == CH_P) { C0[2] = -h * b.taup * 0.5; C2[2] = -h * b.taup * 0.1; }
+  else if (kind == CH_N) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); }
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     const double V2 = C2[j], V1 = C1[j] - m1 * V2, V0 = C0[j] - m0 * V1;
@@ -647,32 +706,31 @@ __device__ __forceinline__ void factor_reg(const DevCosmo& c, const Lane& ln, co
 #pragma unroll
   for (int j = 0; j < 4; j++) { sPi[j] = shfl_d(f.beta2[j], lT); t1[j] = shfl_d(f.beta1[j], lT); }
   sPi[2] += shfl_d(f.beta2[2] + f.beta0[2], lP);
-  const double Oc = c.s[BOLT_S_Omega_c] / b.a, Ob = c.s[BOLT_S_Omega_b] / b.a;
+  const double Oc = b.Oc_a, Ob = b.Ob_a;
   const double hk = f.hkap;
   const double dPhi_y[4] = {h, 0, 0, 0};
   const double dDel_y[4] = {-3.0 * h, -hk * hk * f.vden, 0, 0};
   const double dDb_y[4] = {-3.0 * h, 0, 0, hk};
-  double M[4][4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    M[0][j] = dPhi_y[j] + b.cPsi * sPsi[j] + (j == 1 ? 1.0 : 0.0);
-    M[1][j] = (j == 0 ? 1.0 : 0.0) - (j == 1 ? 1.0 : 0.0) + b.k2 * dPhi_y[j] - b.gPhi * (Oc * dDel_y[j] + Ob * dDb_y[j] + sPhi[j]);
-    M[2][j] = (j == 2 ? 1.0 : 0.0) - sPi[j];
-    M[3][j] = (j == 3 ? (1.0 + h - h * b.taup * b.R) : 0.0) + hk * ((j == 1 ? 1.0 : 0.0) + b.csb2 * dDb_y[j]) + f.e4c * t1[j];
+    f.M[0][j] = dPhi_y[j] + b.cPsi * sPsi[j] + (j == 1 ? 1.0 : 0.0);
+    f.M[1][j] = (j == 0 ? 1.0 : 0.0) - (j == 1 ? 1.0 : 0.0) + b.k2 * dPhi_y[j] - b.gPhi * (Oc * dDel_y[j] + Ob * dDb_y[j] + sPhi[j]);
+    f.M[2][j] = (j == 2 ? 1.0 : 0.0) - sPi[j];
+    f.M[3][j] = (j == 3 ? (1.0 + h - h * b.taup * b.R) : 0.0) + hk * ((j == 1 ? 1.0 : 0.0) + b.csb2 * dDb_y[j]) + f.e4c * t1[j];
   }
-  inv4(M, f.inv);
 }
 
 // Solve W U = r for the lane's chain in rr[] (registers, overwritten by U) and the 5 scalars in r5[] (every lane
 // holds the same copy).
-template <int MAXLEN>
-__device__ __forceinline__ void solve_reg(const DevCosmo& c, const Lane& ln, const Bg& b, const RegFactor<MAXLEN>& f,
-                                          double (&rr)[MAXLEN], double (&r5)[5]) {
+template <class TR>
+__device__ __forceinline__ void solve_reg(const Lane& ln, const BgS& b, const RegFactor<TR>& f,
+                                          double (&rr)[TR::MAXLEN > 0 ? TR::MAXLEN : 1], double (&r5)[5]) {
+  constexpr int MAXLEN = TR::MAXLEN;
+  const int kind = ln.kind;
   double ibn = 0.0, rn = 0.0;
 #pragma unroll
   for (int l = MAXLEN - 1; l >= 3; l--) {
-    const bool top = (l == ln.len - 1);
-    const double up = top ? 0.0 : f.hk * (1.0 - RLc(l));
+    const double up = TR::top(kind, l) ? 0.0 : f.hk * (1.0 - RLc(l));
     const double v = rr[l] - (up * ibn) * rn;
     rr[l] = v; rn = v; ibn = f.ibv[l];
   }
@@ -686,16 +744,14 @@ __device__ __forceinline__ void solve_reg(const DevCosmo& c, const Lane& ln, con
   const double sPi = shfl_d(a2, lT) + shfl_d(a2 + a0, lP);
   const double t1 = shfl_d(a1, lT);
   const double rPhi = r5[0], rdel = r5[1], rv = r5[2], rdb = r5[3], rvb = r5[4];
-  const double Oc = c.s[BOLT_S_Omega_c] / b.a, Ob = c.s[BOLT_S_Omega_b] / b.a;
   const double hk = f.hkap, h = f.h;
   const double vc = rv * f.vden, dc = rdel + hk * vc;
   double rhs[4], y[4];
   rhs[0] = -(rPhi + b.cPsi * sPsi);
-  rhs[1] = -(b.k2 * rPhi - b.gPhi * (Oc * dc + Ob * rdb + sPhi));
+  rhs[1] = -(b.k2 * rPhi - b.gPhi * (b.Oc_a * dc + b.Ob_a * rdb + sPhi));
   rhs[2] = sPi;
   rhs[3] = -(hk * b.csb2 * rdb + f.e4c * t1 - rvb);
-#pragma unroll
-  for (int i = 0; i < 4; i++) y[i] = f.inv[i][0] * rhs[0] + f.inv[i][1] * rhs[1] + f.inv[i][2] * rhs[2] + f.inv[i][3] * rhs[3];
+  ge4(f.M, rhs, y);
   r5[0] = rPhi + h * y[0];
   const double v = vc - hk * f.vden * y[1];
   r5[1] = rdel + hk * v - 3.0 * h * y[0];
@@ -709,8 +765,7 @@ __device__ __forceinline__ void solve_reg(const DevCosmo& c, const Lane& ln, con
   double Up = U2;
 #pragma unroll
   for (int l = 3; l < MAXLEN; l++) {
-    const bool top = (l == ln.len - 1);
-    const double lo = top ? -f.hk : -f.hk * RLc(l);
+    const double lo = TR::top(kind, l) ? -f.hk : -f.hk * RLc(l);
     const double U = (rr[l] - lo * Up) * f.ibv[l];
     rr[l] = U; Up = U;
   }
@@ -718,7 +773,7 @@ __device__ __forceinline__ void solve_reg(const DevCosmo& c, const Lane& ln, con
 
 // Chain ownership of a lane for cosmology c.  MAXLEN == 0: generic layout = the reference's unpack order.
 // MAXLEN > 0: interleaved layout [l][chain] (+5 scalars after MAXLEN*NCH) for the register-resident solver.
-template <int MAXLEN, int NQ>
+template <class TR>
 __device__ __forceinline__ void lane_setup(const DevCosmo& c, const SolveParams& p, Lane& ln) {
   ln.lane = threadIdx.x; ln.nq = c.nq; ln.L = p.L; ln.n = p.n;
   ln.riS = 2 * (p.L + 1) + (p.Lnu + 1) + (p.Lm + 1) * c.nq;
@@ -730,22 +785,27 @@ __device__ __forceinline__ void lane_setup(const DevCosmo& c, const SolveParams&
   else if (ln.lane == c.nq + 1) { ln.kind = CH_P; ln.rbase = p.L + 1; ln.rstride = 1; ln.len = p.L + 1; }
   else if (ln.lane == c.nq + 2) { ln.kind = CH_N; ln.rbase = 2 * (p.L + 1); ln.rstride = 1; ln.len = p.Lnu + 1; }
   else { ln.kind = CH_IDLE; ln.rbase = 0; ln.rstride = 0; ln.len = 0; }
-  if constexpr (MAXLEN > 0) { ln.base = (ln.kind == CH_IDLE) ? 0 : ln.lane; ln.stride = (ln.kind == CH_IDLE) ? 0 : NQ + 3; ln.iS = MAXLEN * (NQ + 3); }
+  if constexpr (TR::MAXLEN > 0) { ln.base = (ln.kind == CH_IDLE) ? 0 : ln.lane; ln.stride = (ln.kind == CH_IDLE) ? 0 : TR::NCH; ln.iS = TR::MAXLEN * TR::NCH; }
   else { ln.base = ln.rbase; ln.stride = ln.rstride; ln.iS = ln.riS; }
 }
 
 // Shared-memory doubles per warp.
-template <int MAXLEN, int NQ>
-__host__ __device__ constexpr int k1_array_len(int n) { return MAXLEN > 0 ? MAXLEN * (NQ + 3) + 8 : n; }
-template <int MAXLEN, int NQ>
-__host__ __device__ constexpr int k1_num_arrays() { return MAXLEN > 0 ? 7 : 9; }
+template <class TR>
+__host__ __device__ constexpr int k1_array_len(int n) { return TR::MAXLEN > 0 ? TR::MAXLEN * TR::NCH + 8 : n; }
+template <class TR>
+__host__ __device__ constexpr int k1_num_arrays() { return TR::MAXLEN > 0 ? 7 : 9; }
 
-template <int MAXLEN, int NQ>
-__global__ void __launch_bounds__(32) hierarchy_kernel_t(SolveParams p) {
+// K1_MINBLOCKS: resident warps per SM the register allocator must allow.  8 (255 registers, no spills) measured faster than
+// 12 or 16 (168 / 128 registers with ~1-2 KB of spills) in both the latency- and the throughput-bound regime (profiles/).
+#ifndef K1_MINBLOCKS
+#define K1_MINBLOCKS 8
+#endif
+template <class TR>
+__global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolveParams p) {
   extern __shared__ double sm[];
-  constexpr int NCH = NQ + 3;
+  constexpr int NCH = TR::NCH, MAXLEN = TR::MAXLEN;
   const int n = p.n;
-  const int na = k1_array_len<MAXLEN, NQ>(n);
+  const int na = k1_array_len<TR>(n);
   Lane ln;
   const bool fixed = (p.mode == BOLT_MODE_FIXED);
   const double reltol = p.reltol, abstol = p.abstol;
@@ -757,7 +817,7 @@ __global__ void __launch_bounds__(32) hierarchy_kernel_t(SolveParams p) {
     if (w >= p.nk) break;
     const int ik = p.order[w];
     const DevCosmo& c = *p.cos_list[ik / p.nk_per];
-    lane_setup<MAXLEN, NQ>(c, p, ln);
+    lane_setup<TR>(c, p, ln);
     ln.k = p.k[ik];
     const double x_begin = c.x0, x_end = 0.0;
 
@@ -850,7 +910,9 @@ __global__ void __launch_bounds__(32) hierarchy_kernel_t(SolveParams p) {
       bool accept = true; double EEst = 0.0, q11 = 0.0;
       if constexpr (MAXLEN > 0) {
         // ---------------- register-resident stages ----------------
-        RegFactor<MAXLEN> f;
+        RegFactor<TR> f;
+        BgS bf;
+        ModeConst mc; mode_const(c, ln, mc);
         double rr[MAXLEN], rh[MAXLEN], r5[5], rh5[5];
         const int lo_ = ln.lane;   // lane offset inside a row of the interleaved layout
         for (int s = 1; s < 6; s++) {
@@ -859,7 +921,7 @@ __global__ void __launch_bounds__(32) hierarchy_kernel_t(SolveParams p) {
 #pragma unroll
           for (int l = 0; l < MAXLEN; l++) {
             double v = 0.0;
-            if (l < ln.len) {
+            if (TR::act(ln.kind, l)) {
               const int idx = lo_ + l * NCH;
               v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
             }
@@ -871,19 +933,17 @@ __global__ void __launch_bounds__(32) hierarchy_kernel_t(SolveParams p) {
             const double v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
             r5[j] = v; rh5[j] = v;
           }
-          eval_bg(c, ln, x + KC_C[s] * dt, bs);
-          rsa_flag |= (ln.k * bs.eta > 240.0) && (-bs.taup * bs.H / bs.eta > 100.0);
-          factor_reg<MAXLEN>(c, ln, bs, KC_GAMMA * dt, f);
-          solve_reg<MAXLEN>(c, ln, bs, f, rr, r5);
+          eval_bg_fast(c, ln, mc, x + KC_C[s] * dt, bf);
+          rsa_flag |= (ln.k * bf.eta > 240.0) && (-bf.taup * bf.H > 100.0 * bf.eta);
+          factor_reg<TR>(ln, bf, KC_GAMMA * dt, f);
+          solve_reg<TR>(ln, bf, f, rr, r5);
           double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
-          __syncwarp();
 #pragma unroll
-          for (int l = 0; l < MAXLEN; l++) if (l < ln.len) zout[lo_ + l * NCH] = (rr[l] - rh[l]) * (1.0 / KC_GAMMA);
-          if (ln.lane == 0) {
+          for (int l = 0; l < MAXLEN; l++) if (TR::act(ln.kind, l)) zout[lo_ + l * NCH] = (rr[l] - rh[l]) * (1.0 / KC_GAMMA);
+          // every lane holds identical scalars and stores them itself (same value, same address): a lane later reads
+          // back what it wrote, so no warp-level synchronisation is needed anywhere in the stage loop
 #pragma unroll
-            for (int j = 0; j < 5; j++) zout[ln.iS + j] = (r5[j] - rh5[j]) * (1.0 / KC_GAMMA);
-          }
-          __syncwarp();
+          for (int j = 0; j < 5; j++) zout[ln.iS + j] = (r5[j] - rh5[j]) * (1.0 / KC_GAMMA);
         }
         // error estimate and u_{n+1} = u_n + sum b_j z_j (into the z2 slot)
         {
@@ -891,7 +951,7 @@ __global__ void __launch_bounds__(32) hierarchy_kernel_t(SolveParams p) {
 #pragma unroll
           for (int l = 0; l < MAXLEN; l++) {
             double e = 0.0;
-            if (l < ln.len) {
+            if (TR::act(ln.kind, l)) {
               const int idx = lo_ + l * NCH;
               const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
               e = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
@@ -907,27 +967,24 @@ __global__ void __launch_bounds__(32) hierarchy_kernel_t(SolveParams p) {
             r5[j] = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
             un5[j] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
           }
-          __syncwarp();
-          if (ln.lane == 0) {
 #pragma unroll
-            for (int j = 0; j < 5; j++) Z1[ln.iS + j] = un5[j];
-          }
-          __syncwarp();
+          for (int j = 0; j < 5; j++) Z1[ln.iS + j] = un5[j];
+          __syncwarp();     // the sampling / rotation code below reads other lanes' data
         }
         if (!fixed) {
-          solve_reg<MAXLEN>(c, ln, bs, f, rr, r5);      // smooth_est: W^{-1} err with the last stage's W
+          solve_reg<TR>(ln, bf, f, rr, r5);      // smooth_est: W^{-1} err with the last stage's W
           double ssum = 0.0;
 #pragma unroll
-          for (int l = 0; l < MAXLEN; l++) if (l < ln.len) {
+          for (int l = 0; l < MAXLEN; l++) if (TR::act(ln.kind, l)) {
             const int idx = lo_ + l * NCH;
             const double sc = abstol + reltol * fmax(fabs(U[idx]), fabs(Z1[idx]));
-            const double q = rr[l] / sc; ssum += q * q;
+            const double q = rr[l] * fast_rcp(sc); ssum += q * q;
           }
           if (ln.lane < 5) {
             double e = r5[0]; e = (ln.lane == 1) ? r5[1] : e; e = (ln.lane == 2) ? r5[2] : e; e = (ln.lane == 3) ? r5[3] : e; e = (ln.lane == 4) ? r5[4] : e;
             const int idx = ln.iS + ln.lane;
             const double sc = abstol + reltol * fmax(fabs(U[idx]), fabs(Z1[idx]));
-            const double q = e / sc; ssum += q * q;
+            const double q = e * fast_rcp(sc); ssum += q * q;
           }
           EEst = sqrt(warp_sum(ssum) / n);
         }
