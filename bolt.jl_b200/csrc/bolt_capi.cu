@@ -14,7 +14,10 @@
 
 using namespace bolt;
 
+struct PoolBlock { void* p; size_t bytes; bool used; };
+
 struct bolt_ctx {
+  std::vector<PoolBlock> pool;   // grow-only device workspace cache (cudaMalloc/cudaFree are synchronous and slow)
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
@@ -63,13 +66,33 @@ int fail(bolt_ctx* ctx, int code, const std::string& msg) {
       return fail(ctx, BOLT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
   } while (0)
 
+void* pool_get(bolt_ctx* ctx, size_t bytes) {
+  PoolBlock* best = nullptr;
+  for (auto& b : ctx->pool) if (!b.used && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
+  if (best && best->bytes <= 2 * bytes + (1 << 20)) { best->used = true; return best->p; }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {   // out of memory: drop the idle cache and retry once
+    for (auto it = ctx->pool.begin(); it != ctx->pool.end();) { if (!it->used) { cudaFree(it->p); it = ctx->pool.erase(it); } else ++it; }
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  }
+  ctx->pool.push_back({p, bytes, true});
+  return p;
+}
+void pool_put(bolt_ctx* ctx, void* p) { for (auto& b : ctx->pool) if (b.p == p) { b.used = false; return; } }
+
+// Device scratch buffer leased from the context's pool for the duration of one call.
 template <class T>
 struct DevBuf {
-  T* p = nullptr; size_t n = 0;
+  bolt_ctx* ctx = nullptr; T* p = nullptr; size_t n = 0;
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t count) { n = count; return count ? cudaMalloc(&p, count * sizeof(T)) : cudaSuccess; }
+  ~DevBuf() { if (p) pool_put(ctx, p); }
+  cudaError_t alloc(bolt_ctx* c, size_t count) {
+    ctx = c; n = count;
+    if (!count) return cudaSuccess;
+    p = (T*)pool_get(c, count * sizeof(T));
+    return p ? cudaSuccess : cudaErrorMemoryAllocation;
+  }
 };
 
 bool g_const_init[64] = {false};
@@ -144,7 +167,7 @@ int upload_k_sorted(bolt_ctx* ctx, const double* k, int nk, DevBuf<double>& d_k,
   std::vector<int> order(nk);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return k[a] > k[b]; });   // longest solves first
-  CUDA_OK(d_k.alloc(nk)); CUDA_OK(d_order.alloc(nk));
+  CUDA_OK(d_k.alloc(ctx, nk)); CUDA_OK(d_order.alloc(ctx, nk));
   CUDA_OK(cudaMemcpyAsync(d_k.p, k, nk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_OK(cudaMemcpyAsync(d_order.p, order.data(), nk * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));   // `order` is a local
@@ -178,13 +201,13 @@ int project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, const
   const double xmax = kd_max * h.s[BOLT_S_eta0];    // kgrid[end]*eta0 (spectra.jl:85); quadratic_k ends exactly at kmax
   const double dg = xmax / 5000.0;
   DevBuf<int> d_ell, d_jlo; DevBuf<double> d_J, d_Cf, d_cp, d_iden, d_ks, d_wk, d_wl, d_chi, d_SDT, d_SDP, d_part;
-  CUDA_OK(d_ell.alloc(nell)); CUDA_OK(d_J.alloc((size_t)nell * BESSEL_NB)); CUDA_OK(d_Cf.alloc((size_t)nell * BESSEL_NC));
+  CUDA_OK(d_ell.alloc(ctx, nell)); CUDA_OK(d_J.alloc(ctx, (size_t)nell * BESSEL_NB)); CUDA_OK(d_Cf.alloc(ctx, (size_t)nell * BESSEL_NC));
   CUDA_OK(cudaMemcpyAsync(d_ell.p, ell, nell * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   {  // Thomas multipliers of the (1/6, 2/3, 1/6) interior system
     const int m = BESSEL_NB - 2; std::vector<double> cp(m), iden(m);
     const double a = 1.0 / 6.0, b = 2.0 / 3.0;
     for (int i = 0; i < m; i++) { const double den = (i == 0) ? b : b - a * cp[i - 1]; cp[i] = a / den; iden[i] = 1.0 / den; }
-    CUDA_OK(d_cp.alloc(m)); CUDA_OK(d_iden.alloc(m));
+    CUDA_OK(d_cp.alloc(ctx, m)); CUDA_OK(d_iden.alloc(ctx, m));
     CUDA_OK(cudaMemcpyAsync(d_cp.p, cp.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_OK(cudaMemcpyAsync(d_iden.p, iden.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -196,7 +219,7 @@ int project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, const
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timing[5] += 2;
-  CUDA_OK(d_ks.alloc(nkd1)); CUDA_OK(d_wk.alloc(nkd1)); CUDA_OK(d_wl.alloc(nkd1)); CUDA_OK(d_jlo.alloc(nkd1)); CUDA_OK(d_chi.alloc(nrows));
+  CUDA_OK(d_ks.alloc(ctx, nkd1)); CUDA_OK(d_wk.alloc(ctx, nkd1)); CUDA_OK(d_wl.alloc(ctx, nkd1)); CUDA_OK(d_jlo.alloc(ctx, nkd1)); CUDA_OK(d_chi.alloc(ctx, nrows));
   CUDA_OK(cudaEventRecord(ctx->ev[4], ctx->stream));
   dense_k_kernel<<<(nkd1 + 127) / 128, 128, 0, ctx->stream>>>(d_kc, nk, kd_min, kd_max, n_kd, h.s[BOLT_S_A], h.s[BOLT_S_n], dg,
                                                               d_ks.p, d_wk.p, d_jlo.p, d_wl.p);
@@ -204,16 +227,16 @@ int project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, const
   chi_kernel<<<(nrows + 127) / 128, 128, 0, ctx->stream>>>(c->d, ix_start, nrows, d_chi.p);
   CUDA_OK(cudaGetLastError());
   dim3 gsd((nkd1 + 127) / 128, nrows);
-  if (d_ST) { CUDA_OK(d_SDT.alloc((size_t)nrows * ld));
+  if (d_ST) { CUDA_OK(d_SDT.alloc(ctx, (size_t)nrows * ld));
     dense_source_kernel<<<gsd, 128, 0, ctx->stream>>>(d_ST, h.n_x, ix_start, nrows, d_jlo.p, d_wl.p, nkd1, ld, h.x0, h.dx, d_SDT.p);
     CUDA_OK(cudaGetLastError()); ctx->timing[6] += 1; }
-  if (d_SP) { CUDA_OK(d_SDP.alloc((size_t)nrows * ld));
+  if (d_SP) { CUDA_OK(d_SDP.alloc(ctx, (size_t)nrows * ld));
     dense_source_kernel<<<gsd, 128, 0, ctx->stream>>>(d_SP, h.n_x, ix_start, nrows, d_jlo.p, d_wl.p, nkd1, ld, h.x0, h.dx, d_SDP.p);
     CUDA_OK(cudaGetLastError()); ctx->timing[6] += 1; }
   const int groups = (nell + PROJ_NL - 1) / PROJ_NL;
   int nsplit = (8 * ctx->num_sms + groups - 1) / groups;
   nsplit = std::max(1, std::min(nsplit, std::max(1, nkd1 / PROJ_NT)));
-  CUDA_OK(d_part.alloc((size_t)nell * nsplit * 3));
+  CUDA_OK(d_part.alloc(ctx, (size_t)nell * nsplit * 3));
   ProjectParams pp;
   pp.Cf = d_Cf.p; pp.ells = d_ell.p; pp.nell = nell; pp.chi = d_chi.p; pp.nrows = nrows; pp.kscaled = d_ks.p; pp.wk = d_wk.p;
   pp.nkd1 = nkd1; pp.ld = ld; pp.SD_T = d_SDT.p; pp.SD_P = d_SDP.p; pp.nsplit = nsplit; pp.partial = d_part.p;
@@ -266,6 +289,7 @@ int bolt_finalize(bolt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& e : ctx->ev) cudaEventDestroy(e);
+  for (auto& b : ctx->pool) cudaFree(b.p);
   cudaFree(ctx->d_counter);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -351,11 +375,11 @@ int bolt_solve(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, cons
   const int n = bolt_state_dim(o->l_gamma, o->l_nu, o->l_mnu, c->h.nq), n_x = c->h.n_x;
   DevBuf<double> d_k, d_ST, d_SP, d_hist, d_final; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns, d_nr;
   rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
-  if (S_T) { CUDA_OK(d_ST.alloc((size_t)nk * n_x)); CUDA_OK(cudaMemsetAsync(d_ST.p, 0, d_ST.n * 8, ctx->stream)); }
-  if (S_P) { CUDA_OK(d_SP.alloc((size_t)nk * n_x)); CUDA_OK(cudaMemsetAsync(d_SP.p, 0, d_SP.n * 8, ctx->stream)); }
-  if (u_hist) { CUDA_OK(d_hist.alloc((size_t)nk * n_x * n)); CUDA_OK(cudaMemsetAsync(d_hist.p, 0, d_hist.n * 8, ctx->stream)); }
-  if (u_final) CUDA_OK(d_final.alloc((size_t)nk * n));
-  CUDA_OK(d_status.alloc(nk)); CUDA_OK(d_ns.alloc(nk)); CUDA_OK(d_nr.alloc(nk));
+  if (S_T) { CUDA_OK(d_ST.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemsetAsync(d_ST.p, 0, d_ST.n * 8, ctx->stream)); }
+  if (S_P) { CUDA_OK(d_SP.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemsetAsync(d_SP.p, 0, d_SP.n * 8, ctx->stream)); }
+  if (u_hist) { CUDA_OK(d_hist.alloc(ctx, (size_t)nk * n_x * n)); CUDA_OK(cudaMemsetAsync(d_hist.p, 0, d_hist.n * 8, ctx->stream)); }
+  if (u_final) CUDA_OK(d_final.alloc(ctx, (size_t)nk * n));
+  CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk)); CUDA_OK(d_nr.alloc(ctx, nk));
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, o, d_ST.p, d_SP.p, d_hist.p, d_final.p, d_status.p, d_ns.p, d_nr.p);
   if (rc) return rc;
   if (S_T) CUDA_OK(cudaMemcpyAsync(S_T, d_ST.p, d_ST.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -389,11 +413,11 @@ int bolt_project(bolt_ctx* ctx, const bolt_cosmo* c, const double* S_T, const do
   CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
   const int n_x = c->h.n_x;
   DevBuf<double> d_k, d_ST, d_SP, d_cl;
-  CUDA_OK(d_k.alloc(nk));
+  CUDA_OK(d_k.alloc(ctx, nk));
   CUDA_OK(cudaMemcpyAsync(d_k.p, k, nk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (S_T) { CUDA_OK(d_ST.alloc((size_t)nk * n_x)); CUDA_OK(cudaMemcpyAsync(d_ST.p, S_T, d_ST.n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
-  if (S_P) { CUDA_OK(d_SP.alloc((size_t)nk * n_x)); CUDA_OK(cudaMemcpyAsync(d_SP.p, S_P, d_SP.n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
-  CUDA_OK(d_cl.alloc((size_t)3 * nell));
+  if (S_T) { CUDA_OK(d_ST.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemcpyAsync(d_ST.p, S_T, d_ST.n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
+  if (S_P) { CUDA_OK(d_SP.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemcpyAsync(d_SP.p, S_P, d_SP.n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
+  CUDA_OK(d_cl.alloc(ctx, (size_t)3 * nell));
   int rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, ell, nell, kd_min, kd_max, n_kd, ix_start, d_cl.p);
   if (rc) return rc;
   if (cl_tt && S_T) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -416,8 +440,8 @@ int bolt_spectra(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, co
   const int n_x = c->h.n_x;
   DevBuf<double> d_k, d_ST, d_SP, d_cl; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns;
   rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
-  CUDA_OK(d_ST.alloc((size_t)nk * n_x)); CUDA_OK(d_SP.alloc((size_t)nk * n_x));
-  CUDA_OK(d_status.alloc(nk)); CUDA_OK(d_ns.alloc(nk)); CUDA_OK(d_cl.alloc((size_t)3 * nell));
+  CUDA_OK(d_ST.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(d_SP.alloc(ctx, (size_t)nk * n_x));
+  CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk)); CUDA_OK(d_cl.alloc(ctx, (size_t)3 * nell));
   bolt_opts oo = *o;
   oo.ix_first = std::max(oo.ix_first, ix_start);    // the LOS sum only reads rows >= ix_start (spectra.jl:86)
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, d_ST.p, d_SP.p, nullptr, nullptr, d_status.p, d_ns.p, nullptr);
@@ -445,7 +469,7 @@ int bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const
   const int n = bolt_state_dim(o->l_gamma, o->l_nu, o->l_mnu, c->h.nq);
   DevBuf<double> d_k, d_final, d_pk; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns;
   rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
-  CUDA_OK(d_final.alloc((size_t)nk * n)); CUDA_OK(d_pk.alloc(nk)); CUDA_OK(d_status.alloc(nk)); CUDA_OK(d_ns.alloc(nk));
+  CUDA_OK(d_final.alloc(ctx, (size_t)nk * n)); CUDA_OK(d_pk.alloc(ctx, nk)); CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk));
   bolt_opts oo = *o; oo.ix_first = c->h.n_x;   // plin only needs perturb(0): no source sampling
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, nullptr, nullptr, nullptr, d_final.p, d_status.p, d_ns.p, nullptr);
   if (rc) return rc;
@@ -499,7 +523,7 @@ int bolt_fp64_peak(bolt_ctx* ctx, double* tflops) {
   if (!ctx || !tflops) return BOLT_ERR_ARG;
   CUDA_OK(cudaSetDevice(ctx->device));
   const int blocks = ctx->num_sms * 8, threads = 256, iters = 1 << 15;
-  DevBuf<double> d_out; CUDA_OK(d_out.alloc((size_t)blocks * threads));
+  DevBuf<double> d_out; CUDA_OK(d_out.alloc(ctx, (size_t)blocks * threads));
   double best = 0.0;
   for (int rep = 0; rep < 4; rep++) {
     CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
