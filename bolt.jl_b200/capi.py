@@ -15,7 +15,7 @@ _LIB = None
 
 EXPORTS = ["bolt_abi_version", "bolt_init", "bolt_finalize", "bolt_last_error", "bolt_last_timing",
            "bolt_cosmo_upload", "bolt_cosmo_free", "bolt_state_dim", "bolt_solve", "bolt_project",
-           "bolt_spectra", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak"]
+           "bolt_spectra", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak", "bolt_set_bessel_xmax"]
 
 
 class BoltError(RuntimeError):
@@ -45,6 +45,7 @@ def lib():
                                    C.c_int, C.c_int, dp, dp, dp, ip, lp]
         L.bolt_plin.argtypes = [vp, vp, dp, C.c_int, C.POINTER(abi.Opts), dp, ip, lp]
         L.bolt_fp64_peak.argtypes = [vp, dp]
+        L.bolt_set_bessel_xmax.argtypes = [vp, C.c_double]
         L.bolt_solve_device.argtypes = [vp, vp, vp, C.c_int, C.POINTER(abi.Opts), vp, vp, vp, vp, vp, vp]
         L.bolt_project_device.argtypes = [vp, vp, vp, vp, vp, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, vp]
         _LIB = L
@@ -71,6 +72,9 @@ class Context:
         lib().bolt_last_timing(self._h, abi.ptr(t))
         return dict(hierarchy_ms=t[0], bessel_ms=t[1], project_ms=t[2], total_ms=t[3],
                     hierarchy_launches=int(t[4]), bessel_launches=int(t[5]), project_launches=int(t[6]))
+
+    def set_bessel_xmax(self, xmax):
+        self.check(lib().bolt_set_bessel_xmax(self._h, float(xmax)))
 
     def fp64_peak_tflops(self):
         t = np.zeros(1)
@@ -113,10 +117,12 @@ class DeviceCosmo:
         nk, n_x = len(k), self.hc.n_x
         n = abi.state_dim(opts.l_gamma, opts.l_nu, opts.l_mnu, self.hc.nq)
         out = {}
-        out["S_T"] = np.zeros((nk, n_x)) if "S_T" in want else None
-        out["S_P"] = np.zeros((nk, n_x)) if "S_P" in want else None
+        nd = self.hc.nd
+        tail = () if nd == 1 else (nd,)      # dual-capable arrays carry a trailing (value, partials...) axis
+        out["S_T"] = np.zeros((nk, n_x) + tail) if "S_T" in want else None
+        out["S_P"] = np.zeros((nk, n_x) + tail) if "S_P" in want else None
         out["u_hist"] = np.zeros((nk, n_x, n)) if "u_hist" in want else None
-        out["u_final"] = np.zeros((nk, n)) if "u_final" in want else None
+        out["u_final"] = np.zeros((nk, n) + tail) if "u_final" in want else None
         out["status"] = np.zeros(nk, dtype=np.int32)
         out["nsteps"] = np.zeros(nk, dtype=np.int64)
         out["nreject"] = np.zeros(nk, dtype=np.int64)
@@ -131,9 +137,10 @@ class DeviceCosmo:
         ells = np.ascontiguousarray(ells, dtype=np.int32)
         S_T = None if S_T is None else np.ascontiguousarray(S_T, dtype=np.float64)
         S_P = None if S_P is None else np.ascontiguousarray(S_P, dtype=np.float64)
-        tt = np.zeros(len(ells)) if S_T is not None else None
-        ee = np.zeros(len(ells)) if S_P is not None else None
-        te = np.zeros(len(ells)) if (S_T is not None and S_P is not None) else None
+        shp = (len(ells),) if self.hc.nd == 1 else (len(ells), self.hc.nd)
+        tt = np.zeros(shp) if S_T is not None else None
+        ee = np.zeros(shp) if S_P is not None else None
+        te = np.zeros(shp) if (S_T is not None and S_P is not None) else None
         self.ctx.check(lib().bolt_project(self.ctx._h, self._h, abi.ptr(S_T), abi.ptr(S_P), abi.ptr(k), len(k),
                                           abi.ptr(ells, abi.c_int32_p), len(ells), kd_min, kd_max, n_kd, ix_start,
                                           abi.ptr(tt), abi.ptr(te), abi.ptr(ee)))
@@ -142,7 +149,8 @@ class DeviceCosmo:
     def spectra(self, k, opts, ells, kd_min, kd_max, n_kd, ix_start):
         k = np.ascontiguousarray(k, dtype=np.float64)
         ells = np.ascontiguousarray(ells, dtype=np.int32)
-        tt, te, ee = np.zeros(len(ells)), np.zeros(len(ells)), np.zeros(len(ells))
+        shp = (len(ells),) if self.hc.nd == 1 else (len(ells), self.hc.nd)
+        tt, te, ee = np.zeros(shp), np.zeros(shp), np.zeros(shp)
         st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
         self.ctx.check(lib().bolt_spectra(self.ctx._h, self._h, abi.ptr(k), len(k), C.byref(opts),
                                           abi.ptr(ells, abi.c_int32_p), len(ells), kd_min, kd_max, n_kd, ix_start,
@@ -152,7 +160,8 @@ class DeviceCosmo:
 
     def plin(self, k, opts):
         k = np.ascontiguousarray(k, dtype=np.float64)
-        pk = np.zeros(len(k)); st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
+        pk = np.zeros(len(k) if self.hc.nd == 1 else (len(k), self.hc.nd))
+        st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
         self.ctx.check(lib().bolt_plin(self.ctx._h, self._h, abi.ptr(k), len(k), C.byref(opts), abi.ptr(pk),
                                        abi.ptr(st, abi.c_int32_p), abi.ptr(ns, abi.c_int64_p)))
         return pk, st, ns

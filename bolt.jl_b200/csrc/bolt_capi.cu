@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "hierarchy_kernel.cuh"
+#include "hierarchy_dual.cuh"
 #include "projection_kernel.cuh"
 
 using namespace bolt;
@@ -25,6 +26,7 @@ struct bolt_ctx {
   std::string err;
   double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int* d_counter = nullptr;
+  double bessel_xmax = 0.0;  // 0: kgrid[end]*eta0 (src/spectra.jl:85); > 0: caller-fixed table range (bolt_set_bessel_xmax)
   double* d_dbg = nullptr;   // step log (only when BOLT_DEBUG_STEPS is set)
 };
 constexpr int DBG_CAP = 1 << 16;
@@ -33,6 +35,7 @@ struct bolt_cosmo {
   DevCosmo h;              // host copy (table pointers are device pointers)
   DevCosmo* d = nullptr;   // device copy
   double* d_tables = nullptr;
+  double* d_dtables = nullptr;         // partial tables [NTABLES][np][n_x+2] (nd > 1)
   const DevCosmo** d_list = nullptr;   // device array {d}: the 1-cosmology work list of K1
 };
 
@@ -113,7 +116,6 @@ int check_opts(bolt_ctx* ctx, const bolt_cosmo* c, const bolt_opts* o) {
   if (o->l_gamma > MAX_L || o->l_nu > MAX_L || o->l_mnu > MAX_L) return fail(ctx, BOLT_ERR_ARG, "truncation too large");
   if (o->mode == BOLT_MODE_FIXED && !(o->fixed_dt > 0)) return fail(ctx, BOLT_ERR_ARG, "fixed_dt must be > 0");
   if (o->mode == BOLT_MODE_ADAPTIVE && !(o->reltol > 0 && o->abstol > 0)) return fail(ctx, BOLT_ERR_ARG, "tolerances must be > 0");
-  if (c->h.nd != 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "dual partials (nd > 1) are not implemented in this build");
   return BOLT_OK;
 }
 
@@ -136,9 +138,29 @@ int launch_k1(bolt_ctx* ctx, const SolveParams& p) {
   return BOLT_OK;
 }
 
+template <int NP>
+int launch_k1_dual(bolt_ctx* ctx, const SolveParams& p) {
+  auto kern = hierarchy_dual_kernel<NP>;
+  const size_t smem = k1_dual_smem_doubles<NP>(p.n) * sizeof(double);
+  if (smem > 227 * 1024) return fail(ctx, BOLT_ERR_UNSUPPORTED, "state x partials does not fit in shared memory");
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int occ = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+  if (occ < 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "state x partials does not fit in shared memory");
+  const int grid = std::max(1, std::min(p.nk, occ * ctx->num_sms));
+  CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  kern<<<grid, 32, smem, ctx->stream>>>(p);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->timing[4] += 1;
+  return BOLT_OK;
+}
+
 // Launch K1 on device buffers.  cos_list: device array of ncos cosmology pointers; work item g (0 <= g < nk) belongs to
 // cosmology g / nk_per.
-int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int nk_per, const double* d_k, const int* d_order, int nk,
+int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int np, int nk_per, const double* d_k, const int* d_order, int nk,
                      const bolt_opts* o, double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status,
                      long long* d_nsteps, long long* d_nreject) {
   SolveParams p;
@@ -150,6 +172,14 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   p.S_T = d_ST; p.S_P = d_SP; p.u_hist = d_hist; p.u_final = d_final;
   p.status = d_status; p.nsteps = d_nsteps; p.nreject = d_nreject; p.counter = ctx->d_counter;
   p.dbg = ctx->d_dbg; p.dbg_cap = ctx->d_dbg ? DBG_CAP : 0;
+  if (np > 0) {     // value + gradient in one pass (hierarchy_dual.cuh)
+    switch (np) {
+#define BOLT_DUAL_CASE(N) case N: return launch_k1_dual<N>(ctx, p);
+      BOLT_DUAL_CASE(1) BOLT_DUAL_CASE(2) BOLT_DUAL_CASE(3) BOLT_DUAL_CASE(4) BOLT_DUAL_CASE(6)
+#undef BOLT_DUAL_CASE
+      default: return fail(ctx, BOLT_ERR_UNSUPPORTED, "this build carries 1, 2, 3, 4 or 6 partials per call");
+    }
+  }
   const bool force_generic = getenv("BOLT_K1_GENERIC") != nullptr;     // development switch
   if (!force_generic && nq == 15 && p.Lnu == 8 && p.Lm == 10) {          // source_grid's truncations (src/spectra.jl:11)
     if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15>>(ctx, p);         // l_gamma = 8: the reference default
@@ -160,7 +190,7 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
 int launch_hierarchy(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, const int* d_order, int nk, const bolt_opts* o,
                      double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status, long long* d_nsteps,
                      long long* d_nreject) {
-  return launch_hierarchy(ctx, c->d_list, c->h.nq, nk, d_k, d_order, nk, o, d_ST, d_SP, d_hist, d_final, d_status, d_nsteps, d_nreject);
+  return launch_hierarchy(ctx, c->d_list, c->h.nq, c->h.np, nk, d_k, d_order, nk, o, d_ST, d_SP, d_hist, d_final, d_status, d_nsteps, d_nreject);
 }
 
 int upload_k_sorted(bolt_ctx* ctx, const double* k, int nk, DevBuf<double>& d_k, DevBuf<int>& d_order) {
@@ -186,6 +216,67 @@ void reset_timing(bolt_ctx* ctx) { for (int i = 0; i < 8; i++) ctx->timing[i] = 
 
 constexpr int PROJ_NL = 4, PROJ_NT = 512;
 
+constexpr int PROJD_NL = 2, PROJD_NT = 256;
+
+template <int NP>
+int launch_project_dual(bolt_ctx* ctx, const ProjectParamsD& pd, int groups, int nsplit, size_t smem) {
+  auto kern = project_kernel_dual<PROJD_NL, PROJD_NT, NP>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(groups, nsplit), PROJD_NT, smem, ctx->stream>>>(pd);
+  CUDA_OK(cudaGetLastError());
+  return BOLT_OK;
+}
+
+// K2 with partials.  Sources are [nk][n_x][nd]; d_cl = [3][nell][nd].
+int project_device_dual(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, const double* d_SP, int nell, int ix_start, int nrows,
+                        int nkd1, int ld, double dg, const int* d_ell, const double* d_Cf, const double* d_ks, const double* d_wk,
+                        const int* d_jlo, const double* d_wl, double* d_cl) {
+  const DevCosmo& h = c->h;
+  const int np = h.np, nd = 1 + np;
+  const size_t cstr = (size_t)nrows * ld;
+  DevBuf<double> d_chi, d_dwk, d_SDT, d_SDP, d_part, d_partd;
+  CUDA_OK(d_chi.alloc(ctx, (size_t)nd * nrows)); CUDA_OK(d_dwk.alloc(ctx, (size_t)np * nkd1));
+  chi_kernel_nd<<<(nrows + 127) / 128, 128, 0, ctx->stream>>>(c->d, ix_start, nrows, d_chi.p);
+  CUDA_OK(cudaGetLastError());
+  dense_k_partials_kernel<<<(nkd1 + 127) / 128, 128, 0, ctx->stream>>>(c->d, d_ks, dg, d_wk, nkd1, d_dwk.p);
+  CUDA_OK(cudaGetLastError());
+  dim3 gsd((nkd1 + 127) / 128, nrows);
+  if (d_ST) { CUDA_OK(d_SDT.alloc(ctx, (size_t)nd * cstr));
+    for (int q = 0; q < nd; q++) dense_source_kernel_nd<<<gsd, 128, 0, ctx->stream>>>(d_ST, h.n_x, nd, q, ix_start, nrows, d_jlo, d_wl, nkd1, ld, h.x0, h.dx, d_SDT.p + q * cstr);
+    CUDA_OK(cudaGetLastError()); ctx->timing[6] += nd; }
+  if (d_SP) { CUDA_OK(d_SDP.alloc(ctx, (size_t)nd * cstr));
+    for (int q = 0; q < nd; q++) dense_source_kernel_nd<<<gsd, 128, 0, ctx->stream>>>(d_SP, h.n_x, nd, q, ix_start, nrows, d_jlo, d_wl, nkd1, ld, h.x0, h.dx, d_SDP.p + q * cstr);
+    CUDA_OK(cudaGetLastError()); ctx->timing[6] += nd; }
+  const int groups = (nell + PROJD_NL - 1) / PROJD_NL;
+  int nsplit = (8 * ctx->num_sms + groups - 1) / groups;
+  nsplit = std::max(1, std::min(nsplit, std::max(1, nkd1 / PROJD_NT)));
+  CUDA_OK(d_part.alloc(ctx, (size_t)nell * nsplit * 3)); CUDA_OK(d_partd.alloc(ctx, (size_t)nell * nsplit * 3 * np));
+  ProjectParamsD pd;
+  pd.v.Cf = d_Cf; pd.v.ells = d_ell; pd.v.nell = nell; pd.v.chi = d_chi.p; pd.v.nrows = nrows; pd.v.kscaled = d_ks; pd.v.wk = d_wk;
+  pd.v.nkd1 = nkd1; pd.v.ld = ld; pd.v.SD_T = d_SDT.p; pd.v.SD_P = d_SDP.p; pd.v.nsplit = nsplit; pd.v.partial = d_part.p;
+  pd.chi_d = d_chi.p + nrows; pd.dwk = d_dwk.p; pd.SD_T_d = d_ST ? d_SDT.p + cstr : nullptr; pd.SD_P_d = d_SP ? d_SDP.p + cstr : nullptr;
+  pd.partial_d = d_partd.p;
+  const size_t smem = ((size_t)PROJD_NL * BESSEL_NC + (size_t)nd * nrows) * sizeof(double);
+  int rc;
+  switch (np) {
+    case 1: rc = launch_project_dual<1>(ctx, pd, groups, nsplit, smem); break;
+    case 2: rc = launch_project_dual<2>(ctx, pd, groups, nsplit, smem); break;
+    case 3: rc = launch_project_dual<3>(ctx, pd, groups, nsplit, smem); break;
+    case 4: rc = launch_project_dual<4>(ctx, pd, groups, nsplit, smem); break;
+    case 6: rc = launch_project_dual<6>(ctx, pd, groups, nsplit, smem); break;
+    default: return fail(ctx, BOLT_ERR_UNSUPPORTED, "this build carries 1, 2, 3, 4 or 6 partials per call");
+  }
+  if (rc) return rc;
+  cl_finalize_kernel_nd<<<(nell + 127) / 128, 128, 0, ctx->stream>>>(d_part.p, d_partd.p, d_ell, nell, nsplit, np, d_ST ? d_cl : nullptr,
+                                                                     (d_ST && d_SP) ? d_cl + (size_t)nell * nd : nullptr,
+                                                                     d_SP ? d_cl + 2 * (size_t)nell * nd : nullptr);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->timing[6] += 5;
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return BOLT_OK;
+}
+
 // K2 pipeline on device buffers.  d_cl = [3][nell] (tt, te, ee).
 int project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, const double* d_SP, const double* d_kc, int nk,
                    const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start, double* d_cl) {
@@ -198,7 +289,9 @@ int project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, const
   const int nrows = h.n_x - 1 - ix_start;           // x_grid[ix_start .. n_x-2] (spectra.jl:70-76)
   const int nkd1 = n_kd - 1;
   const int ld = (nkd1 + 31) / 32 * 32;
-  const double xmax = kd_max * h.s[BOLT_S_eta0];    // kgrid[end]*eta0 (spectra.jl:85); quadratic_k ends exactly at kmax
+  // kgrid[end]*eta0 (spectra.jl:85; quadratic_k ends exactly at kmax).  The reference strips partials from this range
+  // (assume_nondual, spectra.jl:52): the table GRID is not differentiated.
+  const double xmax = ctx->bessel_xmax > 0.0 ? ctx->bessel_xmax : kd_max * h.s[BOLT_S_eta0];
   const double dg = xmax / 5000.0;
   DevBuf<int> d_ell, d_jlo; DevBuf<double> d_J, d_Cf, d_cp, d_iden, d_ks, d_wk, d_wl, d_chi, d_SDT, d_SDP, d_part;
   CUDA_OK(d_ell.alloc(ctx, nell)); CUDA_OK(d_J.alloc(ctx, (size_t)nell * BESSEL_NB)); CUDA_OK(d_Cf.alloc(ctx, (size_t)nell * BESSEL_NC));
@@ -224,6 +317,8 @@ int project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, const
   dense_k_kernel<<<(nkd1 + 127) / 128, 128, 0, ctx->stream>>>(d_kc, nk, kd_min, kd_max, n_kd, h.s[BOLT_S_A], h.s[BOLT_S_n], dg,
                                                               d_ks.p, d_wk.p, d_jlo.p, d_wl.p);
   CUDA_OK(cudaGetLastError());
+  if (h.np > 0) return project_device_dual(ctx, c, d_ST, d_SP, nell, ix_start, nrows, nkd1, ld, dg, d_ell.p, d_Cf.p, d_ks.p, d_wk.p,
+                                           d_jlo.p, d_wl.p, d_cl);
   chi_kernel<<<(nrows + 127) / 128, 128, 0, ctx->stream>>>(c->d, ix_start, nrows, d_chi.p);
   CUDA_OK(cudaGetLastError());
   dim3 gsd((nkd1 + 127) / 128, nrows);
@@ -345,6 +440,29 @@ int bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* d, bolt_cosmo** out)
     h.eta_end = ce[i] * (e * e * e / 6.0) + ce[i + 1] * (2.0 / 3.0 - dd * dd + dd * dd * dd / 2.0) +
                 ce[i + 2] * (2.0 / 3.0 - e * e + e * e * e / 2.0) + ce[i + 3] * (dd * dd * dd / 6.0);
   }
+  // forward-mode partials (nd > 1): partial tables component-major, and the log-derivatives of the momentum-grid constants
+  // (T_nu ~ (N_nu rho_crit Om_r)^(1/4); q_i ~ T_nu; wq_i ~ q_i^3; dlnf0dlnq(q_i) depends on q_i/T_nu only: no partials)
+  h.np = nd - 1;
+  if (h.np > MAX_NP) { cudaFree(c->d_tables); delete c; return fail(ctx, BOLT_ERR_UNSUPPORTED, "more than 8 partials"); }
+  for (int t = 0; t < BOLT_NTABLES; t++) h.dtab[t] = nullptr;
+  if (h.np > 0) {
+    const int np = h.np;
+    std::vector<double> dt((size_t)BOLT_NTABLES * np * nc);
+    for (int t = 0; t < BOLT_NTABLES; t++)
+      for (int j = 0; j < np; j++)
+        for (int i = 0; i < nc; i++) dt[((size_t)t * np + j) * nc + i] = d->tables[((size_t)t * nc + i) * nd + 1 + j];
+    if (cudaMalloc(&c->d_dtables, dt.size() * sizeof(double)) != cudaSuccess) { cudaFree(c->d_tables); delete c; return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc partial tables"); }
+    cudaMemcpy(c->d_dtables, dt.data(), dt.size() * sizeof(double), cudaMemcpyHostToDevice);
+    for (int t = 0; t < BOLT_NTABLES; t++) h.dtab[t] = c->d_dtables + (size_t)t * np * nc;
+    const double* ce = dt.data() + (size_t)BOLT_T_eta * np * nc;
+    for (int j = 0; j < np; j++) {
+      for (int i = 0; i < BOLT_NSCALARS; i++) h.ds[i][j] = d->scalars[(size_t)i * nd + 1 + j];
+      const double dlnT = 0.25 * (h.ds[BOLT_S_N_nu][j] / N_nu + h.ds[BOLT_S_rho_crit][j] / rho_crit + h.ds[BOLT_S_Omega_r][j] / Om_r);
+      for (int i = 0; i < h.nq; i++) { h.dq[i][j] = h.q[i] * dlnT; h.dwq[i][j] = 3.0 * h.wq[i] * dlnT; }
+      h.dOmega_nu[j] = h.Omega_nu * (h.ds[BOLT_S_N_nu][j] / N_nu + h.ds[BOLT_S_Omega_r][j] / Om_r);
+      h.deta_end[j] = ce[(size_t)j * nc + h.n_x];     // eta spline at the last knot: c[n] = y[n-1] (Line(OnGrid()) boundary)
+    }
+  }
   if (cudaMalloc(&c->d, sizeof(DevCosmo)) != cudaSuccess) { cudaFree(c->d_tables); delete c; return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc cosmo"); }
   cudaMemcpy(c->d, &h, sizeof(DevCosmo), cudaMemcpyHostToDevice);
   eta_end_kernel<<<1, 1, 0, ctx->stream>>>(c->d);
@@ -358,7 +476,7 @@ int bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* d, bolt_cosmo** out)
 int bolt_cosmo_free(bolt_ctx* ctx, bolt_cosmo* c) {
   if (!c) return BOLT_OK;
   if (ctx) cudaSetDevice(ctx->device);
-  cudaFree(c->d); cudaFree(c->d_tables); cudaFree(c->d_list);
+  cudaFree(c->d); cudaFree(c->d_tables); cudaFree(c->d_dtables); cudaFree(c->d_list);
   delete c;
   return BOLT_OK;
 }
@@ -372,13 +490,14 @@ int bolt_solve(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, cons
   CUDA_OK(cudaSetDevice(ctx->device));
   reset_timing(ctx);
   CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
-  const int n = bolt_state_dim(o->l_gamma, o->l_nu, o->l_mnu, c->h.nq), n_x = c->h.n_x;
+  const int n = bolt_state_dim(o->l_gamma, o->l_nu, o->l_mnu, c->h.nq), n_x = c->h.n_x * c->h.nd;   // n_x: doubles per source column
+  if (u_hist && c->h.nd > 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "u_hist is value-only (nd = 1)");
   DevBuf<double> d_k, d_ST, d_SP, d_hist, d_final; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns, d_nr;
   rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
   if (S_T) { CUDA_OK(d_ST.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemsetAsync(d_ST.p, 0, d_ST.n * 8, ctx->stream)); }
   if (S_P) { CUDA_OK(d_SP.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemsetAsync(d_SP.p, 0, d_SP.n * 8, ctx->stream)); }
   if (u_hist) { CUDA_OK(d_hist.alloc(ctx, (size_t)nk * n_x * n)); CUDA_OK(cudaMemsetAsync(d_hist.p, 0, d_hist.n * 8, ctx->stream)); }
-  if (u_final) CUDA_OK(d_final.alloc(ctx, (size_t)nk * n));
+  if (u_final) CUDA_OK(d_final.alloc(ctx, (size_t)nk * n * c->h.nd));
   CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk)); CUDA_OK(d_nr.alloc(ctx, nk));
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, o, d_ST.p, d_SP.p, d_hist.p, d_final.p, d_status.p, d_ns.p, d_nr.p);
   if (rc) return rc;
@@ -407,22 +526,22 @@ int bolt_project(bolt_ctx* ctx, const bolt_cosmo* c, const double* S_T, const do
                  double* cl_tt, double* cl_te, double* cl_ee) {
   if (!ctx) return BOLT_ERR_ARG;
   if (!c || !k || nk < 2 || !ell || nell < 1 || (!S_T && !S_P)) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
-  if (c->h.nd != 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "dual partials (nd > 1) are not implemented in this build");
   CUDA_OK(cudaSetDevice(ctx->device));
   reset_timing(ctx);
   CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
-  const int n_x = c->h.n_x;
+  const int nd = c->h.nd, n_x = c->h.n_x * nd;     // doubles per source column
   DevBuf<double> d_k, d_ST, d_SP, d_cl;
   CUDA_OK(d_k.alloc(ctx, nk));
   CUDA_OK(cudaMemcpyAsync(d_k.p, k, nk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (S_T) { CUDA_OK(d_ST.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemcpyAsync(d_ST.p, S_T, d_ST.n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
   if (S_P) { CUDA_OK(d_SP.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemcpyAsync(d_SP.p, S_P, d_SP.n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
-  CUDA_OK(d_cl.alloc(ctx, (size_t)3 * nell));
+  const size_t ncl = (size_t)nell * nd;
+  CUDA_OK(d_cl.alloc(ctx, 3 * ncl));
   int rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, ell, nell, kd_min, kd_max, n_kd, ix_start, d_cl.p);
   if (rc) return rc;
-  if (cl_tt && S_T) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (cl_te && S_T && S_P) CUDA_OK(cudaMemcpyAsync(cl_te, d_cl.p + nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (cl_ee && S_P) CUDA_OK(cudaMemcpyAsync(cl_ee, d_cl.p + 2 * (size_t)nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_tt && S_T) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_te && S_T && S_P) CUDA_OK(cudaMemcpyAsync(cl_te, d_cl.p + ncl, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_ee && S_P) CUDA_OK(cudaMemcpyAsync(cl_ee, d_cl.p + 2 * ncl, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return collect_timing(ctx);
@@ -437,20 +556,21 @@ int bolt_spectra(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, co
   CUDA_OK(cudaSetDevice(ctx->device));
   reset_timing(ctx);
   CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
-  const int n_x = c->h.n_x;
+  const int nd = c->h.nd, n_x = c->h.n_x * nd;
+  const size_t ncl = (size_t)nell * nd;
   DevBuf<double> d_k, d_ST, d_SP, d_cl; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns;
   rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
   CUDA_OK(d_ST.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(d_SP.alloc(ctx, (size_t)nk * n_x));
-  CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk)); CUDA_OK(d_cl.alloc(ctx, (size_t)3 * nell));
+  CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk)); CUDA_OK(d_cl.alloc(ctx, 3 * ncl));
   bolt_opts oo = *o;
   oo.ix_first = std::max(oo.ix_first, ix_start);    // the LOS sum only reads rows >= ix_start (spectra.jl:86)
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, d_ST.p, d_SP.p, nullptr, nullptr, d_status.p, d_ns.p, nullptr);
   if (rc) return rc;
   rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, ell, nell, kd_min, kd_max, n_kd, ix_start, d_cl.p);
   if (rc) return rc;
-  if (cl_tt) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (cl_te) CUDA_OK(cudaMemcpyAsync(cl_te, d_cl.p + nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (cl_ee) CUDA_OK(cudaMemcpyAsync(cl_ee, d_cl.p + 2 * (size_t)nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_tt) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_te) CUDA_OK(cudaMemcpyAsync(cl_te, d_cl.p + ncl, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_ee) CUDA_OK(cudaMemcpyAsync(cl_ee, d_cl.p + 2 * ncl, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CUDA_OK(cudaMemcpyAsync(status, d_status.p, nk * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (nsteps) CUDA_OK(cudaMemcpyAsync(nsteps, d_ns.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
@@ -466,16 +586,27 @@ int bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const
   CUDA_OK(cudaSetDevice(ctx->device));
   reset_timing(ctx);
   CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const int nd = c->h.nd;
   const int n = bolt_state_dim(o->l_gamma, o->l_nu, o->l_mnu, c->h.nq);
   DevBuf<double> d_k, d_final, d_pk; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns;
   rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
-  CUDA_OK(d_final.alloc(ctx, (size_t)nk * n)); CUDA_OK(d_pk.alloc(ctx, nk)); CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk));
+  CUDA_OK(d_final.alloc(ctx, (size_t)nk * n * nd)); CUDA_OK(d_pk.alloc(ctx, (size_t)nk * nd));
+  CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk));
   bolt_opts oo = *o; oo.ix_first = c->h.n_x;   // plin only needs perturb(0): no source sampling
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, nullptr, nullptr, nullptr, d_final.p, d_status.p, d_ns.p, nullptr);
   if (rc) return rc;
-  plin_kernel<<<(nk + 127) / 128, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p);
+  const int gb = (nk + 127) / 128;
+  switch (c->h.np) {
+    case 0: plin_kernel<<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
+    case 1: plin_kernel_d<1><<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
+    case 2: plin_kernel_d<2><<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
+    case 3: plin_kernel_d<3><<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
+    case 4: plin_kernel_d<4><<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
+    case 6: plin_kernel_d<6><<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
+    default: return fail(ctx, BOLT_ERR_UNSUPPORTED, "this build carries 1, 2, 3, 4 or 6 partials per call");
+  }
   CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaMemcpyAsync(pk, d_pk.p, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(pk, d_pk.p, (size_t)nk * nd * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CUDA_OK(cudaMemcpyAsync(status, d_status.p, nk * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (nsteps) CUDA_OK(cudaMemcpyAsync(nsteps, d_ns.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
@@ -508,7 +639,6 @@ int bolt_project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_S_T,
                         const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start, double* d_cl) {
   if (!ctx) return BOLT_ERR_ARG;
   if (!c || !d_k || nk < 2 || !ell || nell < 1 || (!d_S_T && !d_S_P) || !d_cl) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
-  if (c->h.nd != 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "dual partials (nd > 1) are not implemented in this build");
   CUDA_OK(cudaSetDevice(ctx->device));
   reset_timing(ctx);
   CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
@@ -536,6 +666,12 @@ int bolt_fp64_peak(bolt_ctx* ctx, double* tflops) {
     if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
   }
   *tflops = best;
+  return BOLT_OK;
+}
+
+int bolt_set_bessel_xmax(bolt_ctx* ctx, double xmax) {
+  if (!ctx || xmax < 0.0) return BOLT_ERR_ARG;
+  ctx->bessel_xmax = xmax;
   return BOLT_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/bolt_cuda.h"
+#include "dual.cuh"
 
 namespace bolt {
 
@@ -21,6 +22,12 @@ struct DevCosmo {
   double wq[MAX_NQ];                 // 4π q_i² f0(q_i)/dxdq(q_i) w_i     perturbations.jl:138-142
   double df0[MAX_NQ];                // dlnf0dlnq(q_i)                    background.jl:27-30
   double eta_end;                    // η(x_grid[end])                    perturbations.jl:401
+  // forward-mode partials (nd = 1 + np > 1 only): same quantities, d/dp_j
+  int np;
+  const double* dtab[BOLT_NTABLES];  // partial tables, component-major [np][n_x+2]
+  double ds[BOLT_NSCALARS][MAX_NP];
+  double dq[MAX_NQ][MAX_NP], dwq[MAX_NQ][MAX_NP];
+  double dOmega_nu[MAX_NP], deta_end[MAX_NP];
 };
 
 // Interpolations.jl BSpline(Cubic(Line(OnGrid()))) on the uniform x grid (src/util.jl:11).

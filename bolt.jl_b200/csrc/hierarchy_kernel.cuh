@@ -395,6 +395,7 @@ __device__ __forceinline__ void rhs_full(const DevCosmo& c, const Lane& ln, cons
   metric_from_chains(ln, b, c0, c2, m, c);
   const double T1 = shfl_d(ln.kind == CH_T ? u[ln.base + ln.stride] : 0.0, ln.nq);
   auto get = [&](int l) { return u[ln.base + l * ln.stride]; };
+  #pragma unroll 1
   for (int l = 0; l < ln.len; l++) du[ln.base + l * ln.stride] = rhs_row(ln, b, m, l, get);
   if (ln.lane == 0) {   // :197-200
     du[iS] = m.dPhi;
@@ -421,20 +422,24 @@ __device__ __forceinline__ void initial_conditions(const DevCosmo& c, const Lane
   if (ln.kind == CH_T) {
     u[ln.base] = T0; u[ln.base + st] = T1; u[ln.base + 2 * st] = T2;
     double prev = T2;
+    #pragma unroll 1
     for (int l = 3; l < ln.len; l++) { prev = -(double)l / (2 * l + 1) * k / (Hx * taup) * prev; u[ln.base + l * st] = prev; }
   } else if (ln.kind == CH_P) {
     u[ln.base] = (5.0 / 4.0) * T2; u[ln.base + st] = -k / (4.0 * Hx * taup) * T2;
     double prev = (1.0 / 4.0) * T2; u[ln.base + 2 * st] = prev;
+    #pragma unroll 1
     for (int l = 3; l < ln.len; l++) { prev = -(double)l / (2 * l + 1) * k / (Hx * taup) * prev; u[ln.base + l * st] = prev; }
   } else if (ln.kind == CH_N) {
     u[ln.base] = T0; u[ln.base + st] = T1; u[ln.base + 2 * st] = N2;
     double prev = N2;
+    #pragma unroll 1
     for (int l = 3; l < ln.len; l++) { prev = k / ((2 * l + 1) * Hx) * prev; u[ln.base + l * st] = prev; }
   } else if (ln.kind == CH_M) {
     const double df0 = ln.df0;
     u[ln.base] = -T0 * df0;
     u[ln.base + st] = -b.eq * T1 * df0;
     double prev = -N2 * df0; u[ln.base + 2 * st] = prev;
+    #pragma unroll 1
     for (int l = 3; l < ln.len; l++) { prev = b.qe * k / ((2 * l + 1) * Hx) * prev; u[ln.base + l * st] = prev; }
   }
   if (ln.lane == 0) {
@@ -467,6 +472,7 @@ __device__ __forceinline__ void sample_sources(const DevCosmo& c, const Lane& ln
   auto herm = [&](int idx) { return hm.c0 * u0[idx] + hm.c1 * u1[idx] + hm.d0 * (s1 * z1[idx]) + hm.d1 * z6[idx]; };
   if (p.u_hist) {
     double* out = p.u_hist + ((size_t)ik * c.n_x + ix) * ln.n;
+    #pragma unroll 1
     for (int l = 0; l < ln.len; l++) out[ln.rbase + l * ln.rstride] = herm(ln.base + l * ln.stride);
     if (ln.lane < 5) out[ln.riS + ln.lane] = herm(ln.iS + ln.lane);
   }
@@ -845,16 +851,14 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
     rhs_full(c, ln, b, U, Z5);          // f(u0) in the z6 slot (plays the role of z6/dt of a previous step)
     bool rsa_flag = (ln.k * b.eta > 240.0) && (-b.taup * b.H / b.eta > 100.0);
 
-    int ix = 0;
+    int ix = 0;     // next x_grid row to sample; row 0 (sol(x0) = u0) is emitted by the first accepted step with theta = 0
     int status = BOLT_K_OK;
     long long nsteps = 0, nreject = 0;
-    // first sample: sol(x0) = u0  (theta = 0)
-    if (ix >= p.ix_first) { Hermite h0 = hermite_weights(0.0); sample_sources(c, ln, p, ik, 0, x_begin, h0, U, U, Z5, 0.0, Z5, rsa_flag); }
-    ix = 1;
 
     double x = x_begin, dt;
     auto sumsq_scaled = [&](const double* num, const double* a0, const double* a1) {
       double s = 0.0;
+      #pragma unroll 1
       for (int l = 0; l < ln.len; l++) {
         const int idx = ln.base + l * ln.stride;
         const double sc = abstol + reltol * fmax(fabs(a0[idx]), fabs(a1[idx]));
@@ -874,11 +878,13 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
       const double d0 = sqrt(sumsq_scaled(U, U, U) / n), d1 = sqrt(sumsq_scaled(Z5, U, U) / n);
       double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
       dt0 = fmin(dt0, x_end - x_begin);
+      #pragma unroll 1
       for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; r[idx] = U[idx] + dt0 * Z5[idx]; }
       if (ln.lane < 5) { const int idx = ln.iS + ln.lane; r[idx] = U[idx] + dt0 * Z5[idx]; }
       __syncwarp();
       Bg b1; eval_bg(c, ln, x_begin + dt0, b1);
       rhs_full(c, ln, b1, r, Z0);
+      #pragma unroll 1
       for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; Z0[idx] -= Z5[idx]; }
       if (ln.lane < 5) { const int idx = ln.iS + ln.lane; Z0[idx] -= Z5[idx]; }
       __syncwarp();
@@ -915,64 +921,65 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
         ModeConst mc; mode_const(c, ln, mc);
         double rr[MAXLEN], rh[MAXLEN], r5[5], rh5[5];
         const int lo_ = ln.lane;   // lane offset inside a row of the interleaved layout
-        for (int s = 1; s < 6; s++) {
-          // branch-free assembly: coefficients of stages >= s are zero
-          const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
+        for (int s = 1; s <= 6; s++) {
+          if (s <= 5) {
+            // branch-free assembly: coefficients of stages >= s are zero
+            const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
 #pragma unroll
-          for (int l = 0; l < MAXLEN; l++) {
-            double v = 0.0;
-            if (TR::act(ln.kind, l)) {
-              const int idx = lo_ + l * NCH;
-              v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
+            for (int l = 0; l < MAXLEN; l++) {
+              double v = 0.0;
+              if (TR::act(ln.kind, l)) {
+                const int idx = lo_ + l * NCH;
+                v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
+              }
+              rr[l] = v; rh[l] = v;
             }
-            rr[l] = v; rh[l] = v;
-          }
 #pragma unroll
-          for (int j = 0; j < 5; j++) {
-            const int idx = ln.iS + j;
-            const double v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
-            r5[j] = v; rh5[j] = v;
-          }
-          eval_bg_fast(c, ln, mc, x + KC_C[s] * dt, bf);
-          rsa_flag |= (ln.k * bf.eta > 240.0) && (-bf.taup * bf.H > 100.0 * bf.eta);
-          factor_reg<TR>(ln, bf, KC_GAMMA * dt, f);
-          solve_reg<TR>(ln, bf, f, rr, r5);
-          double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
+            for (int j = 0; j < 5; j++) {
+              const int idx = ln.iS + j;
+              const double v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
+              r5[j] = v; rh5[j] = v;
+            }
+            eval_bg_fast(c, ln, mc, x + KC_C[s] * dt, bf);
+            rsa_flag |= (ln.k * bf.eta > 240.0) && (-bf.taup * bf.H > 100.0 * bf.eta);
+            factor_reg<TR>(ln, bf, KC_GAMMA * dt, f);
+          } else {
+            // "stage 7": error estimate err = sum (b - bhat)_j z_j, smoothed below by W^{-1} of the last stage (smooth_est);
+            // u_{n+1} = u_n + sum b_j z_j goes to the z2 slot, which is free once err is formed
+            const double e0 = KC_E[0] * s1, b0 = KC_A[5][0] * s1;
 #pragma unroll
-          for (int l = 0; l < MAXLEN; l++) if (TR::act(ln.kind, l)) zout[lo_ + l * NCH] = (rr[l] - rh[l]) * (1.0 / KC_GAMMA);
-          // every lane holds identical scalars and stores them itself (same value, same address): a lane later reads
-          // back what it wrote, so no warp-level synchronisation is needed anywhere in the stage loop
+            for (int l = 0; l < MAXLEN; l++) {
+              double e = 0.0;
+              if (TR::act(ln.kind, l)) {
+                const int idx = lo_ + l * NCH;
+                const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
+                e = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
+                Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
+              }
+              rr[l] = e;
+            }
 #pragma unroll
-          for (int j = 0; j < 5; j++) zout[ln.iS + j] = (r5[j] - rh5[j]) * (1.0 / KC_GAMMA);
-        }
-        // error estimate and u_{n+1} = u_n + sum b_j z_j (into the z2 slot)
-        {
-          const double e0 = KC_E[0] * s1, b0 = KC_A[5][0] * s1;
-#pragma unroll
-          for (int l = 0; l < MAXLEN; l++) {
-            double e = 0.0;
-            if (TR::act(ln.kind, l)) {
-              const int idx = lo_ + l * NCH;
+            for (int j = 0; j < 5; j++) {
+              const int idx = ln.iS + j;
               const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
-              e = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
+              r5[j] = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
               Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
             }
-            rr[l] = e;
+            if (fixed) break;
           }
-          double un5[5];
+          solve_reg<TR>(ln, bf, f, rr, r5);
+          if (s <= 5) {
+            double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
 #pragma unroll
-          for (int j = 0; j < 5; j++) {
-            const int idx = ln.iS + j;
-            const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
-            r5[j] = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
-            un5[j] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
+            for (int l = 0; l < MAXLEN; l++) if (TR::act(ln.kind, l)) zout[lo_ + l * NCH] = (rr[l] - rh[l]) * (1.0 / KC_GAMMA);
+            // every lane holds identical scalars and stores them itself (same value, same address): a lane later reads
+            // back what it wrote, so no warp-level synchronisation is needed anywhere in the stage loop
+#pragma unroll
+            for (int j = 0; j < 5; j++) zout[ln.iS + j] = (r5[j] - rh5[j]) * (1.0 / KC_GAMMA);
           }
-#pragma unroll
-          for (int j = 0; j < 5; j++) Z1[ln.iS + j] = un5[j];
-          __syncwarp();     // the sampling / rotation code below reads other lanes' data
         }
+        __syncwarp();     // the sampling / rotation code below reads other lanes' data
         if (!fixed) {
-          solve_reg<TR>(ln, bf, f, rr, r5);      // smooth_est: W^{-1} err with the last stage's W
           double ssum = 0.0;
 #pragma unroll
           for (int l = 0; l < MAXLEN; l++) if (TR::act(ln.kind, l)) {
@@ -1034,7 +1041,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
         if (!isfinite(EEst)) { status = BOLT_K_NONFINITE; break; }
         // Controller input floored at 1e-6: below that the estimate is rounding noise of the stiff start-up phase and
         // would make the step sequence implementation-dependent (DESIGN.md "controller"); acceptance uses the raw value.
-        q11 = pow(fmax(EEst, 1e-6), beta1);
+        q11 = exp(beta1 * log(fmax(EEst, 1e-6)));
         accept = EEst <= 1.0;
         if (p.dbg && ik == 0 && ln.lane == 0 && nsteps + nreject < p.dbg_cap) {
           double* d = p.dbg + 4 * (nsteps + nreject); d[0] = x; d[1] = dt; d[2] = EEst; d[3] = accept ? 1.0 : 0.0;
@@ -1058,7 +1065,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
         flipU = !flipU; flipZ = !flipZ; U = SLOT_U; Z1 = SLOT_Z1; Z0 = SLOT_Z0; Z5 = SLOT_Z5;
         if (fixed) { fixed_left--; s1 = 1.0; }
         else {
-          double q = q11 / pow(qold, beta2);
+          double q = q11 * exp(-beta2 * log(qold));
           q = fmax(1.0 / qmax, fmin(1.0 / qmin, q / safety));
           if (q <= 1.2 && q >= 1.0) q = 1.0;
           qold = fmax(EEst, 1e-4);
@@ -1075,6 +1082,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
     if (rsa_flag && status == BOLT_K_OK) status = BOLT_K_RSA_TRIGGERED;
     if (p.u_final) {
       double* out = p.u_final + (size_t)ik * n;
+      #pragma unroll 1
       for (int l = 0; l < ln.len; l++) out[ln.rbase + l * ln.rstride] = U[ln.base + l * ln.stride];
       if (ln.lane < 5) out[ln.riS + ln.lane] = U[ln.iS + ln.lane];
     }

@@ -233,6 +233,184 @@ __global__ void cl_finalize_kernel(const double* __restrict__ partial, const int
   if (ee) ee[e] = 4.0 * M_PI * (c * lfac * lfac);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// K2 with forward-mode partials.  What carries partials (src/spectra.jl:46-47,52,61,66 strip them from the k grids and
+// from the Bessel table range): the sources S(x,k), chi_i = eta0 - eta(x_i) -- so the Bessel ARGUMENT k*chi_i is dual and
+// the spline's derivative is needed -- and the primordial weight A (k/0.05)^(n-1).
+//   dTheta_l/dp = sum_i [ j~'(t_i) * ks * dchi_i/dp * S_i + j~(t_i) * dS_i/dp ] dx_i ,   t_i = ks*chi_i  (index units)
+//   dC_l/dp     = 4 pi sum_k [ 2 Theta dTheta w + Theta^2 dw/dp ]
+// Component-major device layouts: SD[comp][row][k], chi[comp][row], wk[comp][k]; partial[l][split][3][nd].
+// ---------------------------------------------------------------------------------------------------
+__global__ void dense_source_kernel_nd(const double* __restrict__ S, int n_x, int nd, int comp, int ix_start, int nrows,
+                                       const int* __restrict__ jlo, const double* __restrict__ wlerp, int nkd1, int ld, double x0,
+                                       double dx, double* __restrict__ SD) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= nkd1 || i >= nrows) return;
+  const int ix = ix_start + i;
+  const double dxi = (x0 + dx * (ix + 1)) - (x0 + dx * ix);
+  const double w = wlerp[j]; const int lo = jlo[j];
+  const double s = (1.0 - w) * S[((size_t)lo * n_x + ix) * nd + comp] + w * S[((size_t)(lo + 1) * n_x + ix) * nd + comp];
+  SD[(size_t)i * ld + j] = s * dxi;
+}
+
+__global__ void chi_kernel_nd(const DevCosmo* cos, int ix_start, int nrows, double* __restrict__ chi /* [nd][nrows] */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const DevCosmo& c = *cos;
+  const double x = c.x0 + c.dx * (ix_start + i);
+  chi[i] = c.s[BOLT_S_eta0] - spline_eval(c.tab[BOLT_T_eta], c.n_x, c.x0, c.dx, x);
+  for (int j = 0; j < c.np; j++)
+    chi[(size_t)(1 + j) * nrows + i] = c.ds[BOLT_S_eta0][j] - spline_eval(c.dtab[BOLT_T_eta] + (size_t)j * (c.n_x + 2), c.n_x, c.x0, c.dx, x);
+}
+
+// partials of the k weights: d/dp [A (k/0.05)^(n-1) dk/k] = w (dA/A + ln(k/0.05) dn)
+__global__ void dense_k_partials_kernel(const DevCosmo* cos, const double* __restrict__ kscaled, double dg, const double* __restrict__ wk,
+                                        int nkd1, double* __restrict__ dwk /* [np][nkd1] */) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nkd1) return;
+  const DevCosmo& c = *cos;
+  const double k = kscaled[j] * dg, lk = log(k / 0.05), w = wk[j];
+  for (int q = 0; q < c.np; q++) dwk[(size_t)q * nkd1 + j] = w * (c.ds[BOLT_S_A][q] / c.s[BOLT_S_A] + lk * c.ds[BOLT_S_n][q]);
+}
+
+struct ProjectParamsD {
+  ProjectParams v;
+  const double* chi_d;     // [np][nrows]
+  const double* dwk;       // [np][nkd1]
+  const double* SD_T_d;    // [np][nrows][ld] or null
+  const double* SD_P_d;    // [np][nrows][ld] or null
+  double* partial_d;       // [nell][nsplit][3][np]
+};
+
+template <int NL, int NT, int NP>
+__global__ void __launch_bounds__(NT) project_kernel_dual(ProjectParamsD pd) {
+  const ProjectParams& p = pd.v;
+  extern __shared__ double smem[];
+  double* tabs = smem;                                   // [NL][BESSEL_NC]
+  double* chi = smem + (size_t)NL * BESSEL_NC;           // [1+NP][nrows]
+  __shared__ double red[3 * NL * (1 + NP)][NT / 32];
+  const int g = blockIdx.x, split = blockIdx.y;
+  const int e0 = g * NL;
+  for (int idx = threadIdx.x; idx < NL * BESSEL_NC; idx += NT) {
+    const int l = idx / BESSEL_NC, o = idx - l * BESSEL_NC;
+    const int e = min(e0 + l, p.nell - 1);
+    tabs[idx] = p.Cf[(size_t)e * BESSEL_NC + o];
+  }
+  for (int i = threadIdx.x; i < p.nrows; i += NT) {
+    chi[i] = p.chi[i];
+#pragma unroll
+    for (int q = 0; q < NP; q++) chi[(size_t)(1 + q) * p.nrows + i] = pd.chi_d[(size_t)q * p.nrows + i];
+  }
+  __syncthreads();
+  const int per = (p.nkd1 + p.nsplit - 1) / p.nsplit;
+  const int jbeg = split * per, jend = min(p.nkd1, jbeg + per);
+  double acc[3][NL][1 + NP];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int l = 0; l < NL; l++)
+#pragma unroll
+      for (int q = 0; q <= NP; q++) acc[a][l][q] = 0.0;
+  const bool hasT = p.SD_T != nullptr, hasP = p.SD_P != nullptr;
+  const size_t cstr = (size_t)p.nrows * p.ld;
+  for (int j = jbeg + threadIdx.x; j < jend; j += NT) {
+    const double ks = p.kscaled[j];
+    double th[NL][1 + NP], ep[NL][1 + NP];
+#pragma unroll
+    for (int l = 0; l < NL; l++)
+#pragma unroll
+      for (int q = 0; q <= NP; q++) { th[l][q] = 0.0; ep[l][q] = 0.0; }
+    for (int i = 0; i < p.nrows; i++) {
+      const double t = ks * chi[i];
+      int ii = (int)t;
+      ii = min(ii, BESSEL_NB - 2);
+      const double d = t - (double)ii, e = 1.0 - d;
+      const double d2 = d * d, e2 = e * e;
+      const double w0 = e2 * e * (1.0 / 6.0), w1 = 2.0 / 3.0 - d2 + d2 * d * 0.5, w2 = 2.0 / 3.0 - e2 + e2 * e * 0.5, w3 = d2 * d * (1.0 / 6.0);
+      const double g0 = -0.5 * e2, g1 = -2.0 * d + 1.5 * d2, g2 = 2.0 * e - 1.5 * e2, g3 = 0.5 * d2;     // d(weights)/dt
+      const size_t off = (size_t)i * p.ld + j;
+      const double vT = hasT ? __ldg(p.SD_T + off) : 0.0, vP = hasP ? __ldg(p.SD_P + off) : 0.0;
+      double tq[NP], dT[NP], dP[NP];
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        tq[q] = ks * chi[(size_t)(1 + q) * p.nrows + i];
+        dT[q] = hasT ? __ldg(pd.SD_T_d + (size_t)q * cstr + off) : 0.0;
+        dP[q] = hasP ? __ldg(pd.SD_P_d + (size_t)q * cstr + off) : 0.0;
+      }
+#pragma unroll
+      for (int l = 0; l < NL; l++) {
+        const double* c = tabs + l * BESSEL_NC + ii;
+        const double c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+        const double bes = c0 * w0 + c1 * w1 + c2 * w2 + c3 * w3;
+        const double dbes = c0 * g0 + c1 * g1 + c2 * g2 + c3 * g3;
+        th[l][0] += bes * vT; ep[l][0] += bes * vP;
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+          th[l][1 + q] += dbes * tq[q] * vT + bes * dT[q];
+          ep[l][1 + q] += dbes * tq[q] * vP + bes * dP[q];
+        }
+      }
+    }
+    const double w = p.wk[j];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const double T0 = th[l][0], E0 = ep[l][0];
+      acc[0][l][0] += T0 * T0 * w; acc[1][l][0] += T0 * E0 * w; acc[2][l][0] += E0 * E0 * w;
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        const double dw = pd.dwk[(size_t)q * p.nkd1 + j];
+        acc[0][l][1 + q] += 2.0 * T0 * th[l][1 + q] * w + T0 * T0 * dw;
+        acc[1][l][1 + q] += (th[l][1 + q] * E0 + T0 * ep[l][1 + q]) * w + T0 * E0 * dw;
+        acc[2][l][1 + q] += 2.0 * E0 * ep[l][1 + q] * w + E0 * E0 * dw;
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int l = 0; l < NL; l++)
+#pragma unroll
+      for (int q = 0; q <= NP; q++) {
+        const double s = warp_sum(acc[a][l][q]);
+        if (lane == 0) red[(a * NL + l) * (1 + NP) + q][warp] = s;
+      }
+  __syncthreads();
+  if (threadIdx.x < 3 * NL * (1 + NP)) {
+    double s = 0.0;
+    for (int w = 0; w < NT / 32; w++) s += red[threadIdx.x][w];
+    const int q = threadIdx.x % (1 + NP), al = threadIdx.x / (1 + NP), l = al % NL, a = al / NL;
+    const int e = e0 + l;
+    if (e < p.nell) {
+      if (q == 0) p.partial[((size_t)e * p.nsplit + split) * 3 + a] = s;
+      else pd.partial_d[(((size_t)e * p.nsplit + split) * 3 + a) * NP + (q - 1)] = s;
+    }
+  }
+}
+
+// C_l and its partials: out arrays [nell][nd]
+__global__ void cl_finalize_kernel_nd(const double* __restrict__ partial, const double* __restrict__ partial_d, const int* __restrict__ ells,
+                                      int nell, int nsplit, int np, double* __restrict__ tt, double* __restrict__ te, double* __restrict__ ee) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nell) return;
+  const int nd = 1 + np;
+  const double l = (double)ells[e];
+  const double lfac = sqrt((l + 2.0) * (l + 1.0) * l * (l - 1.0));
+  for (int q = 0; q < nd; q++) {
+    double a = 0, b = 0, c = 0;
+    for (int s = 0; s < nsplit; s++) {
+      const size_t base = ((size_t)e * nsplit + s) * 3;
+      if (q == 0) { a += partial[base]; b += partial[base + 1]; c += partial[base + 2]; }
+      else { a += partial_d[base * np + (q - 1)]; b += partial_d[(base + 1) * np + (q - 1)]; c += partial_d[(base + 2) * np + (q - 1)]; }
+    }
+    if (tt) tt[(size_t)e * nd + q] = 4.0 * M_PI * a;
+    if (te) te[(size_t)e * nd + q] = 4.0 * M_PI * (b * lfac);
+    if (ee) ee[(size_t)e * nd + q] = 4.0 * M_PI * (c * lfac * lfac);
+  }
+}
+
 // plin from the state at x = 0 (spectra.jl:163-198), one thread per k
 __global__ void plin_kernel(const DevCosmo* cos, const double* __restrict__ kk, int nk, const double* __restrict__ u_final,
                             int L, int Lnu, int Lm, double* __restrict__ pk) {

@@ -130,6 +130,11 @@ int  bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, cons
  * out[4..7] = launch counts of the same. */
 int  bolt_last_timing(const bolt_ctx* ctx, double* out8);
 
+/* Fix the range [0, xmax] of the 5001-point j_l tables for subsequent projections on this context (0 restores the default
+ * kgrid[end]*eta0, src/spectra.jl:85).  The reference treats that range as non-differentiable (assume_nondual,
+ * src/spectra.jl:46-52); finite-difference checks of gradients must therefore hold it fixed across the +/- runs. */
+int  bolt_set_bessel_xmax(bolt_ctx* ctx, double xmax);
+
 /* Measured DFMA throughput of the device (TFLOP/s): the FP64 roofline denominator. */
 int  bolt_fp64_peak(bolt_ctx* ctx, double* tflops);
 

@@ -1,0 +1,127 @@
+"""Forward-mode partials on the device (nd > 1) against finite differences of the value path.
+
+The reference validates its own ForwardDiff gradients the same way (AD vs central FD, examples/plot_deriv_cl.jl:35-58,
+test/runtests.jl:54-80); it holds no golden gradient vectors, so C_ℓ / P(k) gradient parity is pinned by FD only
+(SURVEY 8c "parity unpinned")."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["Ω_b", "h", "n"]
+
+
+@pytest.fixture(scope="module")
+def dual_setup(gpu_ctx):
+    import bolt_b200 as B
+    from bolt_b200 import capi
+    from bolt_b200.api import host_cosmo_with_partials
+    par = B.CosmoParams()
+    dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, NAMES, rel_step=1e-5)   # small step: k η₀ ~ 3000 makes the sources oscillatory in h
+    dev = dict(dual=capi.DeviceCosmo(gpu_ctx, dual), base=capi.DeviceCosmo(gpu_ctx, base),
+               pm=[(capi.DeviceCosmo(gpu_ctx, p), capi.DeviceCosmo(gpu_ctx, m)) for p, m in pm])
+    gpu_ctx.set_bessel_xmax(1000 * bg.H0 * bg.η0)     # the j_ℓ table grid is not differentiated (spectra.jl:46-52): hold it fixed
+    yield par, bg, dev, steps
+    gpu_ctx.set_bessel_xmax(0.0)
+
+
+def test_k1_value_part_equals_value_only_run(dual_setup):
+    """The controller sees the value part only: carrying partials must not change the values."""
+    from bolt_b200 import abi
+    par, bg, dev, steps = dual_setup
+    ks = np.array([3.0, 120.0]) * bg.H0
+    for o in (abi.make_opts(8, 8, 10, fixed_dt=0.02), abi.make_opts(8, 8, 10, reltol=1e-9, abstol=1e-6)):
+        g = dev["dual"].solve(ks, o, want=("S_T", "S_P", "u_final")); v = dev["base"].solve(ks, o, want=("S_T", "S_P", "u_final"))
+        assert g["S_T"].shape == (2, 2001, 1 + len(NAMES)) and np.all(g["status"] == 0)
+        # fixed step: identical values.  Adaptive: the error norm also runs over the partials (as in the reference), so the
+        # dual run takes at least as many steps and agrees at tolerance level
+        assert np.all(g["nsteps"] >= v["nsteps"] - 2)
+        tol = 1e-10 if o.mode == abi.MODE_FIXED else 1e-4
+        for key in ("S_T", "u_final"):
+            assert np.abs(g[key][..., 0] - v[key]).max() < tol * np.abs(v[key]).max()
+
+
+def test_k1_partials_match_finite_differences(dual_setup):
+    from bolt_b200 import abi
+    par, bg, dev, steps = dual_setup
+    ks = np.array([2.0, 40.0, 300.0]) * bg.H0     # k carries no partials (spectra.jl:46-47,61)
+    o = abi.make_opts(8, 8, 10, fixed_dt=0.01)
+    g = dev["dual"].solve(ks, o, want=("S_T", "S_P", "u_final"))
+    for j, nm in enumerate(NAMES):
+        vp = dev["pm"][j][0].solve(ks, o, want=("S_T", "S_P", "u_final")); vm = dev["pm"][j][1].solve(ks, o, want=("S_T", "S_P", "u_final"))
+        for key, last in (("S_T", 2001), ("S_P", 1980), ("u_final", None)):     # S_P ~ 1/y² is singular at x -> 0: FD is useless there
+            fd = ((vp[key] - vm[key]) / (2 * steps[j]))[:, :last]; ad = g[key][..., 1 + j][:, :last]
+            if nm == "n":
+                assert np.all(ad == 0) and np.all(fd == 0)      # the hierarchy does not know the spectral index
+                continue
+            err = np.abs(ad - fd).max(axis=1) / np.abs(fd).max(axis=1)
+            assert err.max() < 2e-4, (nm, key, err)
+
+
+def test_cl_gradients_match_finite_differences(dual_setup):
+    """north_star: gradients within 1e-3 relative (TT/TE/EE, through K1 + K2 in one pass)."""
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    par, bg, dev, steps = dual_setup
+    ks = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 60)
+    ells = np.array([2, 10, 30, 100, 220, 400, 650, 1000, 1500, 2000], dtype=np.int32)
+    o = abi.make_opts(8, 8, 10, fixed_dt=0.01)
+    args = (ks, o, ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, 1201)
+    tt, te, ee, st, _ = dev["dual"].spectra(*args)
+    assert tt.shape == (len(ells), 1 + len(NAMES)) and np.all(st == 0)
+    btt, bte, bee, _, _ = dev["base"].spectra(*args)
+    assert np.allclose(tt[:, 0], btt, rtol=1e-9) and np.allclose(ee[:, 0], bee, rtol=1e-9)
+    for j, nm in enumerate(NAMES):
+        p = dev["pm"][j][0].spectra(*args); m = dev["pm"][j][1].spectra(*args)
+        for ad, hi, lo, sc in ((tt, p[0], m[0], btt), (ee, p[2], m[2], bee), (te, p[1], m[1], np.sqrt(btt * bee))):
+            fd = (hi - lo) / (2 * steps[j])
+            err = np.abs(ad[:, 1 + j] - fd) / (np.abs(fd) + 1e-3 * np.abs(sc) / abs(getattr(par, nm)))
+            assert err.max() < 1e-3, (nm, err)
+    # Cauchy-Schwarz still holds for the values
+    assert np.all(te[:, 0] ** 2 <= tt[:, 0] * ee[:, 0] * (1 + 1e-12))
+
+
+def test_amplitude_gradient_is_exact(gpu_ctx):
+    """dC_ℓ/dA = C_ℓ/A and dP/dA = P/A exactly (spectra.jl:92,195)."""
+    import bolt_b200 as B
+    from bolt_b200 import abi, capi
+    from bolt_b200.api import host_cosmo_with_partials
+    par = B.CosmoParams()
+    dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, ["A"])
+    dc = capi.DeviceCosmo(gpu_ctx, dual)
+    ks = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 30)
+    ells = np.array([2, 50, 500, 1500], dtype=np.int32)
+    tt, te, ee, st, _ = dc.spectra(ks, abi.make_opts(8, 8, 10, fixed_dt=0.02), ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, 1201)
+    for c in (tt, te, ee):
+        assert np.allclose(c[:, 1] * par.A, c[:, 0], rtol=1e-12)
+    pk, st, _ = dc.plin(np.array([20.0, 400.0]) * bg.H0, abi.make_opts(8, 8, 10, fixed_dt=0.02))
+    assert pk.shape == (2, 2) and np.allclose(pk[:, 1] * par.A, pk[:, 0], rtol=1e-12)
+
+
+def test_plin_gradients_match_finite_differences(dual_setup):
+    from bolt_b200 import abi
+    par, bg, dev, steps = dual_setup
+    ks = np.array([15.0, 150.0, 1500.0]) * bg.H0
+    o = abi.make_opts(12, 12, 10, fixed_dt=0.01)
+    pk, st, _ = dev["dual"].plin(ks, o)
+    assert np.all(st == 0)
+    for j, nm in enumerate(NAMES):
+        fd = (dev["pm"][j][0].plin(ks, o)[0] - dev["pm"][j][1].plin(ks, o)[0]) / (2 * steps[j])
+        assert np.abs(pk[:, 1 + j] / fd - 1).max() < 1e-3, (nm, pk[:, 1 + j], fd)
+
+
+def test_adaptive_gradients_agree_with_fixed_step(dual_setup):
+    """Adaptive mode (reference tolerances): C_ℓ gradients within 1e-3 of a finely resolved fixed-step run."""
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    par, bg, dev, steps = dual_setup
+    ks = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 40)
+    ells = np.array([10, 100, 400, 1000, 1800], dtype=np.int32)
+    a = dev["dual"].spectra(ks, abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6), ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, 1201)
+    f = dev["dual"].spectra(ks, abi.make_opts(8, 8, 10, fixed_dt=0.0025), ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, 1201)
+    pvals = np.array([getattr(par, nm) for nm in NAMES])
+    scale = [f[0][:, 0], np.sqrt(f[0][:, 0] * f[2][:, 0]), f[2][:, 0]]          # TT, sqrt(TT EE) for TE (crosses zero), EE
+    for x, y, sc in zip(a[:3], f[:3], scale):
+        assert (np.abs(x[:, 0] - y[:, 0]) / sc).max() < 1e-3
+        # gradient error in units of C_ℓ/p, i.e. the error of dlnC_ℓ/dlnp
+        assert (np.abs(x[:, 1:] - y[:, 1:]) * np.abs(pvals)[None, :] / sc[:, None]).max() < 1e-3
