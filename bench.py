@@ -111,6 +111,33 @@ def cpu_sample(hcosmo, kstride=50, nell=25):
                        "C++ restatement with zero-skipping dense LU (faster than the reference's dense LU), not Julia"), t_solve + t_proj
 
 
+def gradient_arm(ctx, ells):
+    """BASELINE configs[2] proper: the same C3 workload with forward-mode partials w.r.t. six parameters (value + gradient
+    from one pass, nd = 7).  tau is not a parameter of the reference: the sixth direction is the neutrino mass.
+    One warm-up and one timed step; reported beside the value-only headline, not instead of it."""
+    import bolt_b200 as B
+    from bolt_b200 import abi, capi
+    from bolt_b200.api import host_cosmo_with_partials
+    names = ["Ω_b", "Ω_c", "h", "n", "A", "Σm_ν"]
+    par = synthetic_params(0)
+    dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, names, rel_step=1e-3)
+    dc = capi.DeviceCosmo(ctx, dual)
+    k = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, NK)
+    o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL)
+    ix0 = int(np.argmax(bg.x_grid > -8))
+    out = None
+    for rep in range(2):
+        t0 = time.perf_counter()
+        out = dc.spectra(k, o, ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, ix0)
+        dt = time.perf_counter() - t0
+    tm = ctx.timing()
+    return {"params": names, "nd": 7, "ms_per_step": 1e3 * dt, "spectra_with_gradients_per_s": 1.0 / dt, "kmode_solves_per_s": NK / dt,
+            "kernel_ms": {"hierarchy": tm["hierarchy_ms"], "bessel_tables": tm["bessel_ms"], "projection": tm["project_ms"]},
+            "ode_steps_per_solve": float(out[4].mean()), "failed_modes": int((out[3] != 0).sum()),
+            "note": "host tables' partials by central differences of the Python host generator (the Julia shim passes ForwardDiff "
+                    "partials); error control runs over value and partials like the reference, hence more steps than value-only"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -118,6 +145,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gradients", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -249,6 +277,8 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_sample(hcos[0])
             line["cpu_baseline"] = cb
+        if not args.no_gradients and world == 1:
+            line["gradients"] = gradient_arm(ctx, ells)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
