@@ -449,6 +449,23 @@ __device__ __forceinline__ void initial_conditions(const DevCosmo& c, const Lane
   __syncwarp();
 }
 
+// Per-mode constants of the fast background evaluation
+struct ModeConst {
+  double k, k2_3, c12, H02h, R0, Oc, Ob, mnu;      // k, k^2/3, 12 H0^2/k^2, H0^2/2, 4 Om_r/(3 Om_b), Om_c, Om_b, sum m_nu
+  double q2, iq, wPhi0, wPsi0;                       // lane: q^2, 1/q, weight prefactors (see eval_bg_fast)
+};
+__device__ __forceinline__ void mode_const(const DevCosmo& c, const Lane& ln, ModeConst& mc) {
+  const double H0 = c.s[BOLT_S_H0], rho_crit = c.s[BOLT_S_rho_crit], Om_r = c.s[BOLT_S_Omega_r];
+  mc.k = ln.k; mc.k2_3 = ln.k * ln.k / 3.0; mc.c12 = 12.0 * H0 * H0 / (ln.k * ln.k); mc.H02h = 0.5 * H0 * H0;
+  mc.R0 = 4.0 * Om_r / (3.0 * c.s[BOLT_S_Omega_b]); mc.Oc = c.s[BOLT_S_Omega_c]; mc.Ob = c.s[BOLT_S_Omega_b];
+  mc.mnu = c.s[BOLT_S_Sum_m_nu];
+  mc.q2 = ln.q * ln.q; mc.iq = (ln.kind == CH_M) ? 1.0 / ln.q : 1.0;
+  mc.wPhi0 = 0.0; mc.wPsi0 = 0.0;
+  if (ln.kind == CH_M) { mc.wPhi0 = ln.wq / rho_crit; mc.wPsi0 = ln.wq * mc.q2 / rho_crit * 0.25; }
+  else if (ln.kind == CH_T) { mc.wPhi0 = 4.0 * Om_r; mc.wPsi0 = Om_r; }
+  else if (ln.kind == CH_N) { mc.wPhi0 = 4.0 * c.Omega_nu; mc.wPsi0 = c.Omega_nu; }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One sample of the source grids at x_grid[ix] from the Hermite dense output of the current step
 // (spectra.jl:13-18: u = perturb(x); hierarchy!(du,u,h,x); source_function(du,u,h,x)).
@@ -468,7 +485,7 @@ __device__ __forceinline__ Hermite hermite_weights(double th) {
 
 __device__ __forceinline__ void sample_sources(const DevCosmo& c, const Lane& ln, const SolveParams& p, int ik, int ix, double xs,
                                                const Hermite& hm, const double* u0, const double* u1, const double* z1, double s1,
-                                               const double* z6, bool& rsa_flag) {
+                                               const double* z6, bool& rsa_flag, const ModeConst* mc = nullptr) {
   auto herm = [&](int idx) { return hm.c0 * u0[idx] + hm.c1 * u1[idx] + hm.d0 * (s1 * z1[idx]) + hm.d1 * z6[idx]; };
   if (p.u_hist) {
     double* out = p.u_hist + ((size_t)ik * c.n_x + ix) * ln.n;
@@ -477,12 +494,32 @@ __device__ __forceinline__ void sample_sources(const DevCosmo& c, const Lane& ln
     if (ln.lane < 5) out[ln.riS + ln.lane] = herm(ln.iS + ln.lane);
   }
   if (!p.S_T && !p.S_P) return;
-  Bg b; eval_bg(c, ln, xs, b);
-  // remaining tables of source_function (:347-349): lanes evaluate one each
-  const int which[5] = {BOLT_T_Hpp, BOLT_T_tau, BOLT_T_g, BOLT_T_gp, BOLT_T_gpp};
-  double tv = 0.0;
-  if (ln.lane < 5) tv = spline_eval(c.tab[which[ln.lane]], c.n_x, c.x0, c.dx, xs);
-  const double Hpp = shfl_d(tv, 0), tau = shfl_d(tv, 1), g = shfl_d(tv, 2), gp = shfl_d(tv, 3), gpp = shfl_d(tv, 4);
+  Bg b; double Hpp, tau, g, gp, gpp;
+  if (mc) {
+    // compact variant (register kernel): all 11 tables of hierarchy! + source_function (:168,172,347-349) from ONE spline
+    // site, lanes 0..10 evaluating one table each; divisions hoisted as in eval_bg_fast
+    const int which[11] = {BOLT_T_H, BOLT_T_eta, BOLT_T_taup, BOLT_T_taupp, BOLT_T_csb2, BOLT_T_Hp, BOLT_T_Hpp, BOLT_T_tau, BOLT_T_g, BOLT_T_gp, BOLT_T_gpp};
+    double tv = 0.0;
+    if (ln.lane < 11) tv = spline_eval(c.tab[which[ln.lane]], c.n_x, c.x0, c.dx, xs);
+    b.x = xs; b.H = shfl_d(tv, 0); b.eta = shfl_d(tv, 1); b.taup = shfl_d(tv, 2); b.taupp = shfl_d(tv, 3); b.csb2 = shfl_d(tv, 4);
+    b.Hp = shfl_d(tv, 5); Hpp = shfl_d(tv, 6); tau = shfl_d(tv, 7); g = shfl_d(tv, 8); gp = shfl_d(tv, 9); gpp = shfl_d(tv, 10);
+    b.a = exp(xs);
+    const double ia = 1.0 / b.a, ia2 = ia * ia, iH = 1.0 / b.H, iH2 = iH * iH;
+    b.kappa = mc->k * iH; b.R = mc->R0 * ia; b.cPsi = mc->c12 * ia2; b.gPhi = mc->H02h * iH2; b.k2 = mc->k2_3 * iH2;
+    b.qe = 1.0; b.eq = 1.0;
+    if (ln.kind == CH_M) {
+      const double am = b.a * mc->mnu;
+      const double eps = sqrt(mc->q2 + am * am), ieps = 1.0 / eps;
+      b.qe = ln.q * ieps; b.eq = eps * mc->iq; b.wPhi = mc->wPhi0 * eps * ia2; b.wPsi = mc->wPsi0 * ieps;
+    } else { b.wPhi = mc->wPhi0 * ia2; b.wPsi = mc->wPsi0; }
+  } else {
+    eval_bg(c, ln, xs, b);
+    // remaining tables of source_function (:347-349): lanes evaluate one each
+    const int which[5] = {BOLT_T_Hpp, BOLT_T_tau, BOLT_T_g, BOLT_T_gp, BOLT_T_gpp};
+    double tv = 0.0;
+    if (ln.lane < 5) tv = spline_eval(c.tab[which[ln.lane]], c.n_x, c.x0, c.dx, xs);
+    Hpp = shfl_d(tv, 0); tau = shfl_d(tv, 1); g = shfl_d(tv, 2); gp = shfl_d(tv, 3); gpp = shfl_d(tv, 4);
+  }
   double uL[5] = {0, 0, 0, 0, 0};
   if (ln.kind != CH_IDLE) {
 #pragma unroll
@@ -579,23 +616,6 @@ __device__ __forceinline__ double fast_rcp(double x) {
   double e = fma(-x, y, 1.0); y = fma(y, e, y);
   e = fma(-x, y, 1.0); y = fma(y, e, y);
   return y;
-}
-
-// Per-mode constants of the fast background evaluation
-struct ModeConst {
-  double k, k2_3, c12, H02h, R0, Oc, Ob, mnu;      // k, k^2/3, 12 H0^2/k^2, H0^2/2, 4 Om_r/(3 Om_b), Om_c, Om_b, sum m_nu
-  double q2, iq, wPhi0, wPsi0;                       // lane: q^2, 1/q, weight prefactors (see eval_bg_fast)
-};
-__device__ __forceinline__ void mode_const(const DevCosmo& c, const Lane& ln, ModeConst& mc) {
-  const double H0 = c.s[BOLT_S_H0], rho_crit = c.s[BOLT_S_rho_crit], Om_r = c.s[BOLT_S_Omega_r];
-  mc.k = ln.k; mc.k2_3 = ln.k * ln.k / 3.0; mc.c12 = 12.0 * H0 * H0 / (ln.k * ln.k); mc.H02h = 0.5 * H0 * H0;
-  mc.R0 = 4.0 * Om_r / (3.0 * c.s[BOLT_S_Omega_b]); mc.Oc = c.s[BOLT_S_Omega_c]; mc.Ob = c.s[BOLT_S_Omega_b];
-  mc.mnu = c.s[BOLT_S_Sum_m_nu];
-  mc.q2 = ln.q * ln.q; mc.iq = (ln.kind == CH_M) ? 1.0 / ln.q : 1.0;
-  mc.wPhi0 = 0.0; mc.wPsi0 = 0.0;
-  if (ln.kind == CH_M) { mc.wPhi0 = ln.wq / rho_crit; mc.wPsi0 = ln.wq * mc.q2 / rho_crit * 0.25; }
-  else if (ln.kind == CH_T) { mc.wPhi0 = 4.0 * Om_r; mc.wPsi0 = Om_r; }
-  else if (ln.kind == CH_N) { mc.wPhi0 = 4.0 * c.Omega_nu; mc.wPsi0 = c.Omega_nu; }
 }
 
 // Stage-time background: same quantities as eval_bg with the divisions hoisted (4 reciprocals, 1 exp, 1 sqrt).
@@ -902,6 +922,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
     const long long fixed_total = fixed ? llround((x_end - x_begin) / p.fixed_dt) : 0;
     long long fixed_left = fixed_total;
     const long long max_steps = p.max_steps > 0 ? p.max_steps : 1000000;
+    ModeConst mc; mode_const(c, ln, mc);
 
     while (true) {
       bool clamped = false;
@@ -918,7 +939,6 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
         // ---------------- register-resident stages ----------------
         RegFactor<TR> f;
         BgS bf;
-        ModeConst mc; mode_const(c, ln, mc);
         double rr[MAXLEN], rh[MAXLEN], r5[5], rh5[5];
         const int lo_ = ln.lane;   // lane offset inside a row of the interleaved layout
         for (int s = 1; s <= 6; s++) {
@@ -1056,7 +1076,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
           if (ix >= p.ix_first) {
             double th = (xs - x) / dt; if (th > 1.0) th = 1.0;
             Hermite hm = hermite_weights(th);
-            sample_sources(c, ln, p, ik, ix, xs, hm, U, Z1, Z0, s1, Z5, rsa_flag);
+            sample_sources(c, ln, p, ik, ix, xs, hm, U, Z1, Z0, s1, Z5, rsa_flag, MAXLEN > 0 ? &mc : nullptr);
           }
           ix++;
         }
