@@ -22,6 +22,8 @@ struct bolt_ctx {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;    // j_l tables are independent of K1: they are built concurrently with the hierarchy solve
+  cudaEvent_t ev_tab = nullptr;
   cudaEvent_t ev[8];
   std::string err;
   double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -277,41 +279,61 @@ int project_device_dual(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, 
   return BOLT_OK;
 }
 
-// K2 pipeline on device buffers.  d_cl = [3][nell] (tt, te, ee).
-int project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, const double* d_SP, const double* d_kc, int nk,
-                   const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start, double* d_cl) {
-  const DevCosmo& h = c->h;
-  if (n_kd < 2 || ix_start < 0 || ix_start >= h.n_x - 1) return fail(ctx, BOLT_ERR_ARG, "bad dense grid / ix_start");
+// j_l tables + B-spline prefilter for a set of multipoles (bessel_interpolator, spectra.jl:49-58).  They depend on the
+// cosmology only through the table range, not on the perturbation solve, so bolt_spectra builds them on a second stream
+// while K1 runs.
+struct BesselTabs {
+  DevBuf<int> d_ell; DevBuf<double> d_J, d_Cf, d_cp, d_iden;
+  double dg = 0.0;
+};
+int check_ells(bolt_ctx* ctx, const int32_t* ell, int nell) {
   for (int i = 0; i < nell; i++) {
     if (ell[i] < 0) return fail(ctx, BOLT_ERR_ARG, "negative multipole");
     if (i > 0 && ell[i] <= ell[i - 1]) return fail(ctx, BOLT_ERR_ARG, "multipoles must be strictly increasing");
   }
+  return BOLT_OK;
+}
+int bessel_prepare(bolt_ctx* ctx, const bolt_cosmo* c, const int32_t* ell, int nell, double kd_max, cudaStream_t st, BesselTabs& bt) {
+  int rc = check_ells(ctx, ell, nell); if (rc) return rc;
+  // kgrid[end]*eta0 (spectra.jl:85; quadratic_k ends exactly at kmax).  The reference strips partials from this range
+  // (assume_nondual, spectra.jl:52): the table GRID is not differentiated.
+  const double xmax = ctx->bessel_xmax > 0.0 ? ctx->bessel_xmax : kd_max * c->h.s[BOLT_S_eta0];
+  bt.dg = xmax / 5000.0;
+  CUDA_OK(bt.d_ell.alloc(ctx, nell)); CUDA_OK(bt.d_J.alloc(ctx, (size_t)nell * BESSEL_NB)); CUDA_OK(bt.d_Cf.alloc(ctx, (size_t)nell * BESSEL_NC));
+  const int m = BESSEL_NB - 2;
+  CUDA_OK(bt.d_cp.alloc(ctx, m)); CUDA_OK(bt.d_iden.alloc(ctx, m));
+  {  // Thomas multipliers of the (1/6, 2/3, 1/6) interior system
+    std::vector<double> cp(m), iden(m);
+    const double a = 1.0 / 6.0, b = 2.0 / 3.0;
+    for (int i = 0; i < m; i++) { const double den = (i == 0) ? b : b - a * cp[i - 1]; cp[i] = a / den; iden[i] = 1.0 / den; }
+    CUDA_OK(cudaMemcpyAsync(bt.d_ell.p, ell, nell * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(bt.d_cp.p, cp.data(), m * 8, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(bt.d_iden.p, iden.data(), m * 8, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));      // host staging vectors go out of scope
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev[2], st));
+  bessel_table_kernel<<<(BESSEL_NB + 63) / 64, 64, 0, st>>>(bt.d_ell.p, nell, bt.dg, bt.d_J.p);
+  CUDA_OK(cudaGetLastError());
+  bessel_prefilter_kernel<<<(nell + 31) / 32, 32, 0, st>>>(bt.d_J.p, nell, bt.d_cp.p, bt.d_iden.p, bt.d_Cf.p);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->ev[3], st));
+  CUDA_OK(cudaEventRecord(ctx->ev_tab, st));
+  ctx->timing[5] += 2;
+  return BOLT_OK;
+}
+
+// K2 pipeline on device buffers (tables already prepared, possibly on another stream).  d_cl = [3][nell][nd] (tt, te, ee).
+int project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_ST, const double* d_SP, const double* d_kc, int nk,
+                   BesselTabs& bt, int nell, double kd_min, double kd_max, int n_kd, int ix_start, double* d_cl) {
+  const DevCosmo& h = c->h;
+  if (n_kd < 2 || ix_start < 0 || ix_start >= h.n_x - 1) return fail(ctx, BOLT_ERR_ARG, "bad dense grid / ix_start");
   const int nrows = h.n_x - 1 - ix_start;           // x_grid[ix_start .. n_x-2] (spectra.jl:70-76)
   const int nkd1 = n_kd - 1;
   const int ld = (nkd1 + 31) / 32 * 32;
-  // kgrid[end]*eta0 (spectra.jl:85; quadratic_k ends exactly at kmax).  The reference strips partials from this range
-  // (assume_nondual, spectra.jl:52): the table GRID is not differentiated.
-  const double xmax = ctx->bessel_xmax > 0.0 ? ctx->bessel_xmax : kd_max * h.s[BOLT_S_eta0];
-  const double dg = xmax / 5000.0;
-  DevBuf<int> d_ell, d_jlo; DevBuf<double> d_J, d_Cf, d_cp, d_iden, d_ks, d_wk, d_wl, d_chi, d_SDT, d_SDP, d_part;
-  CUDA_OK(d_ell.alloc(ctx, nell)); CUDA_OK(d_J.alloc(ctx, (size_t)nell * BESSEL_NB)); CUDA_OK(d_Cf.alloc(ctx, (size_t)nell * BESSEL_NC));
-  CUDA_OK(cudaMemcpyAsync(d_ell.p, ell, nell * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  {  // Thomas multipliers of the (1/6, 2/3, 1/6) interior system
-    const int m = BESSEL_NB - 2; std::vector<double> cp(m), iden(m);
-    const double a = 1.0 / 6.0, b = 2.0 / 3.0;
-    for (int i = 0; i < m; i++) { const double den = (i == 0) ? b : b - a * cp[i - 1]; cp[i] = a / den; iden[i] = 1.0 / den; }
-    CUDA_OK(d_cp.alloc(ctx, m)); CUDA_OK(d_iden.alloc(ctx, m));
-    CUDA_OK(cudaMemcpyAsync(d_cp.p, cp.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_OK(cudaMemcpyAsync(d_iden.p, iden.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  }
-  CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  bessel_table_kernel<<<(BESSEL_NB + 63) / 64, 64, 0, ctx->stream>>>(d_ell.p, nell, dg, d_J.p);
-  CUDA_OK(cudaGetLastError());
-  bessel_prefilter_kernel<<<(nell + 31) / 32, 32, 0, ctx->stream>>>(d_J.p, nell, d_cp.p, d_iden.p, d_Cf.p);
-  CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaEventRecord(ctx->ev[3], ctx->stream));
-  ctx->timing[5] += 2;
+  const double dg = bt.dg;
+  DevBuf<int>& d_ell = bt.d_ell; DevBuf<double>& d_Cf = bt.d_Cf;
+  DevBuf<int> d_jlo; DevBuf<double> d_ks, d_wk, d_wl, d_chi, d_SDT, d_SDP, d_part;
+  CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tab, 0));
   CUDA_OK(d_ks.alloc(ctx, nkd1)); CUDA_OK(d_wk.alloc(ctx, nkd1)); CUDA_OK(d_wl.alloc(ctx, nkd1)); CUDA_OK(d_jlo.alloc(ctx, nkd1)); CUDA_OK(d_chi.alloc(ctx, nrows));
   CUDA_OK(cudaEventRecord(ctx->ev[4], ctx->stream));
   dense_k_kernel<<<(nkd1 + 127) / 128, 128, 0, ctx->stream>>>(d_kc, nk, kd_min, kd_max, n_kd, h.s[BOLT_S_A], h.s[BOLT_S_n], dg,
@@ -371,6 +393,8 @@ int bolt_init(int device_ordinal, bolt_ctx** out) {
   if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
+  if (cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
   for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
   if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return BOLT_ERR_ALLOC; }
   if (init_constants(ctx) != BOLT_OK) { delete ctx; return BOLT_ERR_CUDA; }
@@ -386,7 +410,7 @@ int bolt_finalize(bolt_ctx* ctx) {
   for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& b : ctx->pool) cudaFree(b.p);
   cudaFree(ctx->d_counter);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_tab);
   delete ctx;
   return BOLT_OK;
 }
@@ -537,7 +561,9 @@ int bolt_project(bolt_ctx* ctx, const bolt_cosmo* c, const double* S_T, const do
   if (S_P) { CUDA_OK(d_SP.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemcpyAsync(d_SP.p, S_P, d_SP.n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
   const size_t ncl = (size_t)nell * nd;
   CUDA_OK(d_cl.alloc(ctx, 3 * ncl));
-  int rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, ell, nell, kd_min, kd_max, n_kd, ix_start, d_cl.p);
+  BesselTabs bt;
+  int rc = bessel_prepare(ctx, c, ell, nell, kd_max, ctx->stream, bt); if (rc) return rc;
+  rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, bt, nell, kd_min, kd_max, n_kd, ix_start, d_cl.p);
   if (rc) return rc;
   if (cl_tt && S_T) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (cl_te && S_T && S_P) CUDA_OK(cudaMemcpyAsync(cl_te, d_cl.p + ncl, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -564,9 +590,13 @@ int bolt_spectra(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, co
   CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk)); CUDA_OK(d_cl.alloc(ctx, 3 * ncl));
   bolt_opts oo = *o;
   oo.ix_first = std::max(oo.ix_first, ix_start);    // the LOS sum only reads rows >= ix_start (spectra.jl:86)
+  BesselTabs bt;
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, d_ST.p, d_SP.p, nullptr, nullptr, d_status.p, d_ns.p, nullptr);
   if (rc) return rc;
-  rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, ell, nell, kd_min, kd_max, n_kd, ix_start, d_cl.p);
+  // The j_l tables do not depend on K1.  Enqueued AFTER it on a second stream, their blocks are scheduled as K1's persistent
+  // warps retire, i.e. they fill the low-occupancy tail of the hierarchy solve instead of delaying its start.
+  rc = bessel_prepare(ctx, c, ell, nell, kd_max, ctx->stream2, bt); if (rc) return rc;
+  rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, bt, nell, kd_min, kd_max, n_kd, ix_start, d_cl.p);
   if (rc) return rc;
   if (cl_tt) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (cl_te) CUDA_OK(cudaMemcpyAsync(cl_te, d_cl.p + ncl, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -642,7 +672,9 @@ int bolt_project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_S_T,
   CUDA_OK(cudaSetDevice(ctx->device));
   reset_timing(ctx);
   CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
-  int rc = project_device(ctx, c, d_S_T, d_S_P, d_k, nk, ell, nell, kd_min, kd_max, n_kd, ix_start, d_cl);
+  BesselTabs bt;
+  int rc = bessel_prepare(ctx, c, ell, nell, kd_max, ctx->stream, bt); if (rc) return rc;
+  rc = project_device(ctx, c, d_S_T, d_S_P, d_k, nk, bt, nell, kd_min, kd_max, n_kd, ix_start, d_cl);
   if (rc) return rc;
   CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));

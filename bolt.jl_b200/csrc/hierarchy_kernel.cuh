@@ -597,7 +597,9 @@ struct Trunc {
   static constexpr int LG = LG_, LNU = LNU_, LMNU = LMNU_, NQ = NQ_;
   static constexpr int MAXL = (LG_ > LNU_ ? (LG_ > LMNU_ ? LG_ : LMNU_) : (LNU_ > LMNU_ ? LNU_ : LMNU_));
   static constexpr int MAXLEN = (NQ_ > 0) ? MAXL + 1 : 0;     // 0 = generic (runtime) kernel
-  static constexpr int NCH = NQ_ + 3;
+  // row stride of the interleaved shared-memory layout: one private column per LANE (not per chain), so idle lanes and the
+  // padded rows of short chains can run the unguarded, branch-free code on zeros
+  static constexpr int NCH = 32;
   // row l is the truncation row / an existing row of the lane's chain
   static __device__ __forceinline__ bool top(int kind, int l) {
     return (l == LG_ && (kind == CH_T || kind == CH_P)) || (l == LNU_ && kind == CH_N) || (l == LMNU_ && kind == CH_M);
@@ -811,7 +813,7 @@ __device__ __forceinline__ void lane_setup(const DevCosmo& c, const SolveParams&
   else if (ln.lane == c.nq + 1) { ln.kind = CH_P; ln.rbase = p.L + 1; ln.rstride = 1; ln.len = p.L + 1; }
   else if (ln.lane == c.nq + 2) { ln.kind = CH_N; ln.rbase = 2 * (p.L + 1); ln.rstride = 1; ln.len = p.Lnu + 1; }
   else { ln.kind = CH_IDLE; ln.rbase = 0; ln.rstride = 0; ln.len = 0; }
-  if constexpr (TR::MAXLEN > 0) { ln.base = (ln.kind == CH_IDLE) ? 0 : ln.lane; ln.stride = (ln.kind == CH_IDLE) ? 0 : TR::NCH; ln.iS = TR::MAXLEN * TR::NCH; }
+  if constexpr (TR::MAXLEN > 0) { ln.base = ln.lane; ln.stride = TR::NCH; ln.iS = TR::MAXLEN * TR::NCH; }
   else { ln.base = ln.rbase; ln.stride = ln.rstride; ln.iS = ln.riS; }
 }
 
@@ -947,11 +949,8 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
             const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
 #pragma unroll
             for (int l = 0; l < MAXLEN; l++) {
-              double v = 0.0;
-              if (TR::act(ln.kind, l)) {
-                const int idx = lo_ + l * NCH;
-                v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
-              }
+              const int idx = lo_ + l * NCH;      // padded rows / idle lanes hold zeros
+              const double v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
               rr[l] = v; rh[l] = v;
             }
 #pragma unroll
@@ -969,14 +968,10 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
             const double e0 = KC_E[0] * s1, b0 = KC_A[5][0] * s1;
 #pragma unroll
             for (int l = 0; l < MAXLEN; l++) {
-              double e = 0.0;
-              if (TR::act(ln.kind, l)) {
-                const int idx = lo_ + l * NCH;
-                const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
-                e = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
-                Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
-              }
-              rr[l] = e;
+              const int idx = lo_ + l * NCH;
+              const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
+              rr[l] = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
+              Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
             }
 #pragma unroll
             for (int j = 0; j < 5; j++) {
@@ -991,7 +986,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
           if (s <= 5) {
             double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
 #pragma unroll
-            for (int l = 0; l < MAXLEN; l++) if (TR::act(ln.kind, l)) zout[lo_ + l * NCH] = (rr[l] - rh[l]) * (1.0 / KC_GAMMA);
+            for (int l = 0; l < MAXLEN; l++) zout[lo_ + l * NCH] = (rr[l] - rh[l]) * (1.0 / KC_GAMMA);
             // every lane holds identical scalars and stores them itself (same value, same address): a lane later reads
             // back what it wrote, so no warp-level synchronisation is needed anywhere in the stage loop
 #pragma unroll
@@ -1002,7 +997,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
         if (!fixed) {
           double ssum = 0.0;
 #pragma unroll
-          for (int l = 0; l < MAXLEN; l++) if (TR::act(ln.kind, l)) {
+          for (int l = 0; l < MAXLEN; l++) {
             const int idx = lo_ + l * NCH;
             const double sc = abstol + reltol * fmax(fabs(U[idx]), fabs(Z1[idx]));
             const double q = rr[l] * fast_rcp(sc); ssum += q * q;
