@@ -249,9 +249,11 @@ def main():
         # ratio from the accepted count only (lower bound on work)
         fl = nstep_tot * f_step(n)
         roof = {"kernel": "hierarchy_kernel (K1, dominant)", "bound": "fp64", "achieved": fl / (k1_ms * 1e-3) / 1e12, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": fl / (k1_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": fl / (k1_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                "traffic": 1.16e6, "traffic_note": "dram bytes read+write per launch from profiles/r1_k1_hierarchy.md (ncu --set full): K1 is not HBM bound",
                 "peak_source": "DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
-                "note": "algorithmic flop = accepted steps x (182 n + 3300), n = 197 (DESIGN.md); latency-bound by the longest k-mode"}
+                "note": "algorithmic flop = accepted steps x (182 n + 3300), n = 197 (DESIGN.md); ncu: FP64 pipe active 25% of cycles, "
+                        "issue slots 31% -- dependency-latency and instruction-fetch bound at 8 warps/SM (profiles/README.md)"}
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -261,7 +263,7 @@ def main():
         k2_bytes = (2 * 799 * 4999 * 8) + nell * 5003 * 8      # one read of the dense source grids + the spline tables
         k2_terms = 2.0 * nell * 4999 * 799
         roof_k2 = {"kernel": "project_kernel (K2)", "bound": "hbm", "achieved": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                   "unit": "GB/s", "frac": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                   "unit": "GB/s", "frac": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": 2.99e8,
                    "fp64_tflops": 25.0 * k2_terms / 2 * args.steps / (k2_ms * 1e-3) / 1e12,
                    "note": "K2 is FP64/shared-memory-gather bound, not HBM bound (SURVEY 8d): both figures reported"}
         line = {"metric": "kmode_hierarchy_solves_per_s", "value": value, "unit": "k-mode solves/s", "n_gpus": world, "steps": args.steps,

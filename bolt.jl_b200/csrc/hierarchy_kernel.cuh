@@ -941,23 +941,25 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
         // ---------------- register-resident stages ----------------
         RegFactor<TR> f;
         BgS bf;
-        double rr[MAXLEN], rh[MAXLEN], r5[5], rh5[5];
+        double rr[MAXLEN], r5[5];
         const int lo_ = ln.lane;   // lane offset inside a row of the interleaved layout
         for (int s = 1; s <= 6; s++) {
+          double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
           if (s <= 5) {
-            // branch-free assembly: coefficients of stages >= s are zero
+            // branch-free assembly: coefficients of stages >= s are zero.  The right-hand side is parked in the stage's own
+            // z slot (not yet written) so that z_s = (U - rhs)/gamma needs no register copy
             const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
 #pragma unroll
             for (int l = 0; l < MAXLEN; l++) {
               const int idx = lo_ + l * NCH;      // padded rows / idle lanes hold zeros
               const double v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
-              rr[l] = v; rh[l] = v;
+              rr[l] = v; zout[idx] = v;
             }
 #pragma unroll
             for (int j = 0; j < 5; j++) {
               const int idx = ln.iS + j;
               const double v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
-              r5[j] = v; rh5[j] = v;
+              r5[j] = v; zout[idx] = v;
             }
             eval_bg_fast(c, ln, mc, x + KC_C[s] * dt, bf);
             rsa_flag |= (ln.k * bf.eta > 240.0) && (-bf.taup * bf.H > 100.0 * bf.eta);
@@ -984,13 +986,12 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
           }
           solve_reg<TR>(ln, bf, f, rr, r5);
           if (s <= 5) {
-            double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
 #pragma unroll
-            for (int l = 0; l < MAXLEN; l++) zout[lo_ + l * NCH] = (rr[l] - rh[l]) * (1.0 / KC_GAMMA);
+            for (int l = 0; l < MAXLEN; l++) { const int idx = lo_ + l * NCH; zout[idx] = (rr[l] - zout[idx]) * (1.0 / KC_GAMMA); }
             // every lane holds identical scalars and stores them itself (same value, same address): a lane later reads
             // back what it wrote, so no warp-level synchronisation is needed anywhere in the stage loop
 #pragma unroll
-            for (int j = 0; j < 5; j++) zout[ln.iS + j] = (r5[j] - rh5[j]) * (1.0 / KC_GAMMA);
+            for (int j = 0; j < 5; j++) { const int idx = ln.iS + j; zout[idx] = (r5[j] - zout[idx]) * (1.0 / KC_GAMMA); }
           }
         }
         __syncwarp();     // the sampling / rotation code below reads other lanes' data
