@@ -155,6 +155,122 @@ __device__ __forceinline__ void metric_from_chains_d(const Lane& ln, const BgD<N
   m.dPhi = m.Psi - b.k2 * m.Phi + b.gPhi * (cs_d<NP>(c, BOLT_S_Omega_c) / b.a * m.delta + cs_d<NP>(c, BOLT_S_Omega_b) / b.a * m.delta_b + sPhi);
 }
 
+// G = (dA/dp) U for a plain (partial-free) stage value U: same rows as rhs_row_d, but every product is dual-coefficient x
+// double-state (NP+1 multiplies instead of 2NP+1).  Only the partials of the result are used.
+template <int NP> struct MetricG { double Phi, delta, v, delta_b, v_b, Pi; Dual<NP> Psi, dPhi; };
+
+template <int NP, class Get>
+__device__ __forceinline__ Dual<NP> rhs_row_g(const Lane& ln, const BgD<NP>& b, const MetricG<NP>& m, int l, Get get) {
+  typedef Dual<NP> T;
+  const bool photon = (ln.kind == CH_T || ln.kind == CH_P);
+  const T kq = b.kappa * b.qe;
+  if (l == ln.len - 1) {
+    T damp = (double)ln.len / (b.H * b.eta);
+    if (photon) damp = damp - b.taup;
+    return kq * get(l - 1) - damp * get(l);
+  }
+  if (l == 0) {
+    T r = -(kq * get(1));
+    if (ln.kind == CH_M) r = r + m.dPhi * ln.df0;
+    else if (ln.kind == CH_P) r = r + b.taup * (get(0) - m.Pi * 0.5);
+    else r = r - m.dPhi;
+    return r;
+  }
+  const double rl = c_rl[l];
+  T r = kq * (rl * get(l - 1) - (1.0 - rl) * get(l + 1));
+  if (l == 1) {
+    if (ln.kind == CH_M) r = r - b.kappa * (1.0 / 3.0) * b.eq * m.Psi * ln.df0;
+    else if (ln.kind != CH_P) r = r + b.kappa * (1.0 / 3.0) * m.Psi;
+    if (ln.kind == CH_T) r = r + b.taup * (m.v_b * (1.0 / 3.0));
+  }
+  if (photon) r = r + b.taup * (get(l) - (l == 2 ? m.Pi * 0.1 : 0.0));
+  return r;
+}
+
+// Solve W X_j = R_j for NR right-hand sides at once, in place in the NR component arrays W[j] (shared memory), with the
+// factorisation of the current stage.  Same algebra as solve(); the NR dependency chains are interleaved so that they
+// hide each other's latency (the dual kernel runs at 2 warps per SM, so ILP is the only latency hiding there is).
+template <int NR>
+__device__ __forceinline__ void solve_multi(const DevCosmo& c, const Lane& ln, const Bg& b, const Factor& f, const double* ib,
+                                            double* const (&W)[NR]) {
+  double ibn = 0.0, rn[NR];
+#pragma unroll
+  for (int j = 0; j < NR; j++) rn[j] = 0.0;
+#pragma unroll 1
+  for (int l = ln.maxlen - 1; l >= 3; l--) {
+    if (l < ln.len) {
+      const int idx = ln.base + l * ln.stride;
+      const double m = (l < ln.len - 1) ? f.hk * (1.0 - c_rl[l]) * ibn : 0.0;
+#pragma unroll
+      for (int j = 0; j < NR; j++) { const double v = W[j][idx] - m * rn[j]; W[j][idx] = v; rn[j] = v; }
+      ibn = ib[idx];
+    }
+  }
+  double a0[NR], a1[NR], a2[NR];
+  const int i0 = ln.base, i1 = ln.base + ln.stride, i2 = ln.base + 2 * ln.stride;
+  if (ln.kind != CH_IDLE) {
+    const double ib2 = ib[i2], ib1 = ib[i1], ib0 = ib[i0];
+    const double m2 = f.hk * (1.0 - c_rl[2]) * ibn, m1 = f.hk * (1.0 - c_rl[1]) * ib2, m0 = f.hk * ib1;
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+      const double r2 = W[j][i2] - m2 * rn[j];
+      const double r1 = W[j][i1] - m1 * r2;
+      const double r0 = W[j][i0] - m0 * r1;
+      a0[j] = r0 * ib0; a1[j] = (r1 - f.lo1 * a0[j]) * ib1; a2[j] = (r2 - f.lo2 * a1[j]) * ib2;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NR; j++) { a0[j] = 0.0; a1[j] = 0.0; a2[j] = 0.0; }
+  }
+  const int iS = ln.iS;
+  const double Oc = c.s[BOLT_S_Omega_c] / b.a, Ob = c.s[BOLT_S_Omega_b] / b.a;
+  const double hk = f.hkap, h = f.h;
+  double y[NR][4];
+#pragma unroll
+  for (int j = 0; j < NR; j++) {
+    const double sPsi = warp_sum(b.wPsi * a2[j]);
+    const double sPhi = warp_sum(b.wPhi * a0[j]);
+    double pi = 0.0;
+    if (ln.kind == CH_T) pi = a2[j]; else if (ln.kind == CH_P) pi = a2[j] + a0[j];
+    const double sPi = warp_sum(pi);
+    const double t1 = shfl_d(a1[j], ln.nq);
+    const double rPhi = W[j][iS], rdel = W[j][iS + 1], rv = W[j][iS + 2], rdb = W[j][iS + 3], rvb = W[j][iS + 4];
+    const double vc = rv * f.vden, dc = rdel + hk * vc;
+    double rhs[4];
+    rhs[0] = -(rPhi + b.cPsi * sPsi);
+    rhs[1] = -(b.k2 * rPhi - b.gPhi * (Oc * dc + Ob * rdb + sPhi));
+    rhs[2] = sPi;
+    rhs[3] = -(hk * b.csb2 * rdb + f.e4c * t1 - rvb);
+    lu4_solve(f, rhs, y[j]);
+    // scalars (every lane computes the same values; lane 0 stores after the warp has read the inputs)
+    const double Phi = rPhi + h * y[j][0];
+    const double v = vc - hk * f.vden * y[j][1];
+    const double del = rdel + hk * v - 3.0 * h * y[j][0];
+    const double db = rdb - 3.0 * h * y[j][0] + hk * y[j][3];
+    __syncwarp();
+    if (ln.lane == 0) { W[j][iS] = Phi; W[j][iS + 1] = del; W[j][iS + 2] = v; W[j][iS + 3] = db; W[j][iS + 4] = y[j][3]; }
+  }
+  if (ln.kind != CH_IDLE) {
+    double Up[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+      double U0 = a0[j], U1 = a1[j], U2 = a2[j];
+#pragma unroll
+      for (int q = 0; q < 4; q++) { U0 += f.beta0[q] * y[j][q]; U1 += f.beta1[q] * y[j][q]; U2 += f.beta2[q] * y[j][q]; }
+      W[j][i0] = U0; W[j][i1] = U1; W[j][i2] = U2; Up[j] = U2;
+    }
+#pragma unroll 1
+    for (int l = 3; l < ln.len; l++) {
+      const int idx = ln.base + l * ln.stride;
+      const double lo = (l == ln.len - 1) ? -f.hk : -f.hk * c_rl[l];
+      const double ibl = ib[idx];
+#pragma unroll
+      for (int j = 0; j < NR; j++) { const double U = (W[j][idx] - lo * Up[j]) * ibl; W[j][idx] = U; Up[j] = U; }
+    }
+  }
+  __syncwarp();
+}
+
 // du = A(x;p) u in dual arithmetic.  zero_state_partials = true evaluates on (u, 0): the partials of the result are then
 // G_j = (dA/dp_j) u, the inhomogeneity of the sensitivity equations.
 template <int NP>
@@ -431,47 +547,60 @@ __global__ void __launch_bounds__(32) hierarchy_dual_kernel(SolveParams p) {
         rsa_flag |= (ln.k * bs.eta > 240.0) && (-bs.taup * bs.H / bs.eta > 100.0);
         factor(c, ln, bs, h, ib, f);
         solve(c, ln, bs, f, ib, r, zout.p, rhs0);
-        // ---- G_j = (dA/dp_j) U: the right-hand side in dual arithmetic on (U, 0); U is in r[] ----
+        // ---- G_j = (dA/dp_j) U: rows of the right-hand side with dual coefficients on the plain stage value U (in r[]) ----
         eval_bg_d<NP>(c, ln, xs, bd);
         {
-          auto ld = [&](int idx) { return T(r[idx]); };
-          MetricD<NP> m;
+          MetricG<NP> m;
           const int iS = ln.iS;
-          m.Phi = ld(iS); m.delta = ld(iS + 1); m.v = ld(iS + 2); m.delta_b = ld(iS + 3); m.v_b = ld(iS + 4);
-          T c0(0.0), c2(0.0);
-          if (ln.kind != CH_IDLE) { c0 = ld(ln.base); c2 = ld(ln.base + 2 * ln.stride); }
-          metric_from_chains_d<NP>(ln, bd, c0, c2, m, c);
-          const T T1 = shfl_T(ln.kind == CH_T ? ld(ln.base + ln.stride) : T(0.0), ln.nq);
-          auto get = [&](int l) { return ld(ln.base + l * ln.stride); };
-          // zout partial components <- h * G_j  (they become the sensitivity right-hand sides below)
+          m.Phi = r[iS]; m.delta = r[iS + 1]; m.v = r[iS + 2]; m.delta_b = r[iS + 3]; m.v_b = r[iS + 4];
+          double c0 = 0.0, c2 = 0.0;
+          if (ln.kind != CH_IDLE) { c0 = r[ln.base]; c2 = r[ln.base + 2 * ln.stride]; }
+          const T sPsi = warp_sum_T(bd.wPsi * c2), sPhi = warp_sum_T(bd.wPhi * c0);
+          double pi = 0.0;
+          if (ln.kind == CH_T) pi = c2; else if (ln.kind == CH_P) pi = c2 + c0;
+          m.Pi = warp_sum(pi);
+          m.Psi = -(bd.cPsi * sPsi) - m.Phi;
+          m.dPhi = m.Psi - bd.k2 * m.Phi + bd.gPhi * (cs_d<NP>(c, BOLT_S_Omega_c) * (m.delta / bd.a) + cs_d<NP>(c, BOLT_S_Omega_b) * (m.delta_b / bd.a) + sPhi);
+          const double T1 = shfl_d(ln.kind == CH_T ? r[ln.base + ln.stride] : 0.0, ln.nq);
+          auto get = [&](int l) { return r[ln.base + l * ln.stride]; };
+          // zout partial components <- r_j + h * G_j: the right-hand sides of the sensitivity systems, solved in place below
 #pragma unroll 1
           for (int l = 0; l < ln.len; l++) {
             const int idx = ln.base + l * ln.stride;
-            const T g = rhs_row_d<NP>(ln, bd, m, l, get);
+            const T g = rhs_row_g<NP>(ln, bd, m, l, get);
 #pragma unroll
-            for (int j = 0; j < NP; j++) zout.p[(size_t)(1 + j) * n + idx] = h * g.d[j];
+            for (int j = 0; j < NP; j++) zout.p[(size_t)(1 + j) * n + idx] = rhs_comp(1 + j, idx) + h * g.d[j];
           }
           if (ln.lane == 0) {
-            const T g0 = m.dPhi, g1 = bd.kappa * m.v - 3.0 * m.dPhi, g2 = -m.v - bd.kappa * m.Psi, g3 = bd.kappa * m.v_b - 3.0 * m.dPhi;
-            const T g4 = -m.v_b - bd.kappa * (m.Psi + bd.csb2 * m.delta_b) + bd.taup * bd.R * (3.0 * T1 + m.v_b);
+            const T g0 = m.dPhi, g1 = bd.kappa * m.v - 3.0 * m.dPhi, g2 = -(bd.kappa * m.Psi) - m.v, g3 = bd.kappa * m.v_b - 3.0 * m.dPhi;
+            const T g4 = -(bd.kappa * (m.Psi + bd.csb2 * m.delta_b)) + bd.taup * bd.R * (3.0 * T1 + m.v_b) - m.v_b;
 #pragma unroll
             for (int j = 0; j < NP; j++) {
               double* zp = zout.p + (size_t)(1 + j) * n + iS;
-              zp[0] = h * g0.d[j]; zp[1] = h * g1.d[j]; zp[2] = h * g2.d[j]; zp[3] = h * g3.d[j]; zp[4] = h * g4.d[j];
+              zp[0] = rhs_comp(1 + j, iS) + h * g0.d[j]; zp[1] = rhs_comp(1 + j, iS + 1) + h * g1.d[j]; zp[2] = rhs_comp(1 + j, iS + 2) + h * g2.d[j];
+              zp[3] = rhs_comp(1 + j, iS + 3) + h * g3.d[j]; zp[4] = rhs_comp(1 + j, iS + 4) + h * g4.d[j];
             }
           }
           __syncwarp();
         }
-        // ---- partials: W S_j = r_j + h G_j with the same factorisation ----
+        // ---- partials: W S_j = r_j + h G_j, all NP systems at once with the same factorisation; then z_{s,j} = (S_j - r_j)/gamma ----
+        {
+          double* Wp[NP];
+#pragma unroll
+          for (int j = 0; j < NP; j++) Wp[j] = zout.comp(1 + j);
+          solve_multi<NP>(c, ln, bs, f, ib, Wp);
 #pragma unroll 1
-        for (int j = 1; j <= NP; j++) {
-          double* zj = zout.comp(j);
-          auto rhsj = [&](int idx) { return rhs_comp(j, idx); };
-#pragma unroll 1
-          for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; r[idx] = rhsj(idx) + zj[idx]; }
-          if (ln.lane < 5) { const int idx = ln.iS + ln.lane; r[idx] = rhsj(idx) + zj[idx]; }
+          for (int l = 0; l < ln.len; l++) {
+            const int idx = ln.base + l * ln.stride;
+#pragma unroll
+            for (int j = 0; j < NP; j++) Wp[j][idx] = (Wp[j][idx] - rhs_comp(1 + j, idx)) * (1.0 / KC_GAMMA);
+          }
+          if (ln.lane < 5) {
+            const int idx = ln.iS + ln.lane;
+#pragma unroll
+            for (int j = 0; j < NP; j++) Wp[j][idx] = (Wp[j][idx] - rhs_comp(1 + j, idx)) * (1.0 / KC_GAMMA);
+          }
           __syncwarp();
-          solve(c, ln, bs, f, ib, r, zj, rhsj);      // z_{s,j} = (S_j - r_j)/gamma
         }
       }
       // u_{n+1} for every component (into the z2 slot) -- the error vectors are formed per component below
@@ -495,29 +624,38 @@ __global__ void __launch_bounds__(32) hierarchy_dual_kernel(SolveParams p) {
         // by abstol + reltol*max(|u_n|,|u_{n+1}|) with |.| taken over (value, partials).  Each component's estimate
         // sum (b-bhat)_j z_j is smoothed by W^{-1} of the last stage (smooth_est) with the factorisation in hand.
         const double e0 = KC_E[0] * s1;
-        auto none = [&](int) { return 0.0; };
         auto elem_scale = [&](int idx) {
           double n0 = 0.0, n1 = 0.0;
-#pragma unroll 1
+#pragma unroll
           for (int j = 0; j < ND; j++) { const double a = U.p[(size_t)j * n + idx], b2 = Z1.p[(size_t)j * n + idx]; n0 += a * a; n1 += b2 * b2; }
           return abstol + reltol * sqrt(fmax(n0, n1));
         };
-        double ssum = 0.0;
-#pragma unroll 1
-        for (int j = 0; j < ND; j++) {
-          auto errj = [&](int idx) {
+        // the z3 slot (logical Z2) is recomputed by the next attempt whether this step is accepted or not: its ND component
+        // arrays become the error vectors, smoothed in place all at once
+        auto errpass = [&](int idx) {
+#pragma unroll
+          for (int j = 0; j < ND; j++) {
             const size_t o = (size_t)j * n + idx;
-            return e0 * Z0.p[o] + KC_E[2] * Z2.p[o] + KC_E[3] * Z3.p[o] + KC_E[4] * Z4.p[o] + KC_E[5] * Z5.p[o];
-          };
+            Z2.p[o] = e0 * Z0.p[o] + KC_E[2] * Z2.p[o] + KC_E[3] * Z3.p[o] + KC_E[4] * Z4.p[o] + KC_E[5] * Z5.p[o];
+          }
+        };
 #pragma unroll 1
-          for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; r[idx] = errj(idx); }
-          if (ln.lane < 5) { const int idx = ln.iS + ln.lane; r[idx] = errj(idx); }
-          __syncwarp();
-          solve(c, ln, bs, f, ib, r, (double*)nullptr, none);
+        for (int l = 0; l < ln.len; l++) errpass(ln.base + l * ln.stride);
+        if (ln.lane < 5) errpass(ln.iS + ln.lane);
+        __syncwarp();
+        double* We[ND];
+#pragma unroll
+        for (int j = 0; j < ND; j++) We[j] = Z2.comp(j);
+        solve_multi<ND>(c, ln, bs, f, ib, We);
+        double ssum = 0.0;
+        auto acc = [&](int idx) {
+          const double isc = 1.0 / elem_scale(idx);
+#pragma unroll
+          for (int j = 0; j < ND; j++) { const double q = We[j][idx] * isc; ssum += q * q; }
+        };
 #pragma unroll 1
-          for (int l = 0; l < ln.len; l++) { const int idx = ln.base + l * ln.stride; const double q = r[idx] / elem_scale(idx); ssum += q * q; }
-          if (ln.lane < 5) { const int idx = ln.iS + ln.lane; const double q = r[idx] / elem_scale(idx); ssum += q * q; }
-        }
+        for (int l = 0; l < ln.len; l++) acc(ln.base + l * ln.stride);
+        if (ln.lane < 5) acc(ln.iS + ln.lane);
         EEst = sqrt(warp_sum(ssum) / n);
         if (!isfinite(EEst)) { status = BOLT_K_NONFINITE; break; }
         q11 = exp(beta1 * log(fmax(EEst, 1e-6)));
