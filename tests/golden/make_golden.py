@@ -23,9 +23,9 @@ def reference_fixtures():
     d = d[:-5][::7]                                   # runtests.jl:41 drops the last 5 rows
     np.savez_compressed(f"{HERE}/recfast_xe.npz", z=d[:, 0], Xe=d[:, 1])
     out = {}
-    for tag in ("p03", "p1"):
+    for tag in ("p001", "p01", "p03", "p1", "p3", "p5", "1p0"):     # only p03 is used by a reference test; the rest are extra pins
         c = np.loadtxt(f"{REF}/zack_N_class_px_k{tag}_nofluid_nonu.dat")
-        sel = np.arange(0, c.shape[1], 4)
+        sel = np.arange(0, c.shape[1], 4 if tag in ("p03", "p1") else 8)
         out[f"x_{tag}"] = c[0, sel]; out[f"k_{tag}"] = c[1, 0]
         out[f"d_b_{tag}"] = c[3, sel]; out[f"phi_{tag}"] = c[7, sel]
     np.savez_compressed(f"{HERE}/class_px.npz", **out)
@@ -55,6 +55,7 @@ def oracle_vectors():
 
 if __name__ == "__main__":
     reference_fixtures()
-    oracle_vectors()
+    if "--fixtures-only" not in sys.argv:
+        oracle_vectors()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -51,6 +51,26 @@ def test_nonu_class_comparison_1e_3(cosmo_nonu):
             assert np.all(np.abs(-d_b / g[f"d_b_{tag}"][::-1] - 1) < 1e-3), tag
 
 
+def test_class_potential_at_all_fixture_wavenumbers(cosmo_nonu):
+    """Extra pins: the six sibling CLASS files of the reference's fixture set (k = 0.001 ... 1 h/Mpc) that no reference test
+    consumes.  Φ(x) against CLASS, scaled by max|Φ| because Φ oscillates through zero at high k."""
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    c = cosmo_nonu
+    g = load_golden("class_px.npz")
+    tags = ("p001", "p01", "p03", "p1", "p3", "p5", "1p0")
+    ks = np.array([c.par.h * float(g[f"k_{t}"]) for t in tags])
+    dc = B.device_cosmo(c.par, c.bg, c.ih)
+    out = dc.solve(ks, abi.make_opts(50, 50, 20, reltol=1e-9, abstol=1e-9), want=("u_hist",))
+    assert np.all(out["status"] == 0)
+    n = out["u_hist"].shape[2]
+    for i, t in enumerate(tags):
+        cx = g[f"x_{t}"][::-1]; ref = g[f"phi_{t}"][::-1]
+        phi = CubicSpline(c.bg.x_grid, out["u_hist"][i, :, n - 5])(cx)
+        err = np.abs(phi - ref).max() / np.abs(ref).max()
+        assert err < 2e-3, (t, err)
+
+
 def test_plin_scalar_and_vector(cosmo):
     """examples/basic_usage.jl:11-14: pL = [plin(k, 𝕡, bg, ih) for k in ks]."""
     import bolt_b200 as B
