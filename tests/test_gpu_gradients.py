@@ -33,9 +33,8 @@ def test_k1_value_part_equals_value_only_run(dual_setup):
     for o in (abi.make_opts(8, 8, 10, fixed_dt=0.02), abi.make_opts(8, 8, 10, reltol=1e-9, abstol=1e-6)):
         g = dev["dual"].solve(ks, o, want=("S_T", "S_P", "u_final")); v = dev["base"].solve(ks, o, want=("S_T", "S_P", "u_final"))
         assert g["S_T"].shape == (2, 2001, 1 + len(NAMES)) and np.all(g["status"] == 0)
-        # fixed step: identical values.  Adaptive: the error norm also runs over the partials (as in the reference), so the
-        # dual run takes at least as many steps and agrees at tolerance level
-        assert np.all(g["nsteps"] >= v["nsteps"] - 2)
+        # fixed step: identical values.  Adaptive: the error norm runs over value and partials and is divided by the total
+        # length n(1+N) like DiffEqBase's, so the step sequence differs from the value-only run: tolerance-level agreement
         tol = 1e-10 if o.mode == abi.MODE_FIXED else 1e-4
         for key in ("S_T", "u_final"):
             assert np.abs(g[key][..., 0] - v[key]).max() < tol * np.abs(v[key]).max()
