@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -101,8 +102,11 @@ struct DevBuf {
 };
 
 bool g_const_init[64] = {false};
+std::mutex g_const_mutex;      // contexts may be created from many host threads (one per thread x device)
 
 int init_constants(bolt_ctx* ctx) {
+  std::lock_guard<std::mutex> lock(g_const_mutex);
+  if (ctx->device >= 64) return fail(ctx, BOLT_ERR_ARG, "device ordinal out of range");
   if (g_const_init[ctx->device]) return BOLT_OK;
   double rl[MAX_L + 1];
   for (int l = 0; l <= MAX_L; l++) rl[l] = (double)l / (double)(2 * l + 1);

@@ -95,3 +95,36 @@ def test_rsa_flagged_for_out_of_envelope_k(cosmo, dev):
     from bolt_b200 import abi
     out = dev.solve(np.array([200.0]), abi.make_opts(8, 8, 10, fixed_dt=0.5), want=("u_final",))
     assert out["status"][0] == abi.K_RSA_TRIGGERED
+
+
+def test_other_momentum_grid_and_truncations(gpu_ctx):
+    """Generality of the kernel beyond the reference defaults: nq = 8 momentum nodes (Background(par; nq=8)), uneven truncations,
+    heavier neutrinos -- the generic (runtime-loop) path against the oracle."""
+    import bolt_b200 as B
+    from bolt_b200 import abi, capi
+    from bolt_b200.host import constants as K
+    from oracle.oracle import OracleCosmo
+    par = B.CosmoParams(Σm_ν=0.3 * K.mass_natural, h=0.65, Ω_c=0.27)
+    bg = B.Background(par, nq=8)
+    ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+    hc = abi.HostCosmo.from_host(par, bg, ih)
+    assert hc.nq == 8
+    dc = capi.DeviceCosmo(gpu_ctx, hc); oc = OracleCosmo(hc)
+    ks = np.array([1.0, 90.0]) * bg.H0
+    o = abi.make_opts(6, 4, 5, fixed_dt=0.01)
+    g = dc.solve(ks, o, want=("S_T", "S_P", "u_hist")); r = oc.solve(ks, o, want=("S_T", "S_P", "u_hist"))
+    assert g["u_hist"].shape[2] == abi.state_dim(6, 4, 5, 8) == 72
+    for i in range(2):
+        assert hist_err(g["u_hist"][i], r["u_hist"][i]) < 1e-8
+        assert np.abs(g["S_T"][i] - r["S_T"][i]).max() < 1e-8 * np.abs(r["S_T"][i]).max()
+
+
+def test_unsupported_partial_count_fails_loudly(cosmo, gpu_ctx):
+    """nd = 6 (five partials) is not instantiated in this build: the call must fail, never silently drop partials."""
+    from bolt_b200 import abi, capi
+    hc = cosmo.hc
+    sc = np.zeros((abi.NSCALARS, 6)); tb = np.zeros(hc.tables.shape[:2] + (6,))
+    sc[:, 0] = hc.scalars[:, 0]; tb[..., 0] = hc.tables[..., 0]
+    dc = capi.DeviceCosmo(gpu_ctx, abi.HostCosmo(sc, hc.quad_pts, hc.quad_wts, tb, hc.x0, hc.dx))
+    with pytest.raises(capi.BoltError, match="partials"):
+        dc.solve(np.array([10.0]) * cosmo.bg.H0, abi.make_opts(8, 8, 10, fixed_dt=0.05), want=("S_T",))
