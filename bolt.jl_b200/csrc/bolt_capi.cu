@@ -12,6 +12,7 @@
 
 #include "hierarchy_kernel.cuh"
 #include "hierarchy_dual.cuh"
+#include "hierarchy_dual_reg.cuh"
 #include "projection_kernel.cuh"
 
 using namespace bolt;
@@ -164,6 +165,25 @@ int launch_k1_dual(bolt_ctx* ctx, const SolveParams& p) {
   return BOLT_OK;
 }
 
+template <class TR, int NP>
+int launch_k1_dual_reg(bolt_ctx* ctx, const SolveParams& p) {
+  auto kern = hierarchy_dual_reg_kernel<TR, NP>;
+  const size_t smem = k1_dualreg_smem_doubles<TR, NP>() * sizeof(double);
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int occ = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+  if (occ < 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "dual state does not fit in shared memory");
+  const int grid = std::max(1, std::min(p.nk, occ * ctx->num_sms));
+  CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  kern<<<grid, 32, smem, ctx->stream>>>(p);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->timing[4] += 1;
+  return BOLT_OK;
+}
+
 // Launch K1 on device buffers.  cos_list: device array of ncos cosmology pointers; work item g (0 <= g < nk) belongs to
 // cosmology g / nk_per.
 int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int np, int nk_per, const double* d_k, const int* d_order, int nk,
@@ -178,8 +198,19 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   p.S_T = d_ST; p.S_P = d_SP; p.u_hist = d_hist; p.u_final = d_final;
   p.status = d_status; p.nsteps = d_nsteps; p.nreject = d_nreject; p.counter = ctx->d_counter;
   p.dbg = ctx->d_dbg; p.dbg_cap = ctx->d_dbg ? DBG_CAP : 0;
-  if (np > 0) {     // value + gradient in one pass (hierarchy_dual.cuh)
-    switch (np) {
+  if (np > 0) {     // value + gradient in one pass
+    if (!getenv("BOLT_K1_GENERIC") && nq == 15 && p.L == 8 && p.Lnu == 8 && p.Lm == 10) {     // register-resident (hierarchy_dual_reg.cuh)
+      typedef Trunc<8, 8, 10, 15, 18> TRD;
+      switch (np) {
+        case 1: return launch_k1_dual_reg<TRD, 1>(ctx, p);
+        case 2: return launch_k1_dual_reg<TRD, 2>(ctx, p);
+        case 3: return launch_k1_dual_reg<TRD, 3>(ctx, p);
+        case 4: return launch_k1_dual_reg<TRD, 4>(ctx, p);
+        case 6: return launch_k1_dual_reg<TRD, 6>(ctx, p);
+        default: break;
+      }
+    }
+    switch (np) {     // any truncation (hierarchy_dual.cuh)
 #define BOLT_DUAL_CASE(N) case N: return launch_k1_dual<N>(ctx, p);
       BOLT_DUAL_CASE(1) BOLT_DUAL_CASE(2) BOLT_DUAL_CASE(3) BOLT_DUAL_CASE(4) BOLT_DUAL_CASE(6)
 #undef BOLT_DUAL_CASE

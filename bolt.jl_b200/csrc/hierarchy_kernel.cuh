@@ -592,14 +592,14 @@ __device__ __forceinline__ void sample_sources(const DevCosmo& c, const Lane& ln
 // the 4x4 border system is kept as a matrix and solved per right-hand side by Gaussian elimination with
 // partial pivoting on the augmented 4x5 system (cheaper than a stored factorisation with permutation logic).
 // ---------------------------------------------------------------------------------------------------
-template <int LG_, int LNU_, int LMNU_, int NQ_>
+template <int LG_, int LNU_, int LMNU_, int NQ_, int NCH_ = 32>
 struct Trunc {
   static constexpr int LG = LG_, LNU = LNU_, LMNU = LMNU_, NQ = NQ_;
   static constexpr int MAXL = (LG_ > LNU_ ? (LG_ > LMNU_ ? LG_ : LMNU_) : (LNU_ > LMNU_ ? LNU_ : LMNU_));
   static constexpr int MAXLEN = (NQ_ > 0) ? MAXL + 1 : 0;     // 0 = generic (runtime) kernel
   // row stride of the interleaved shared-memory layout: one private column per LANE (not per chain), so idle lanes and the
   // padded rows of short chains can run the unguarded, branch-free code on zeros
-  static constexpr int NCH = 32;
+  static constexpr int NCH = NCH_;     // 32 in the value kernel; NQ+3 (compact, idle lanes guarded) in the dual kernel
   // row l is the truncation row / an existing row of the lane's chain
   static __device__ __forceinline__ bool top(int kind, int l) {
     return (l == LG_ && (kind == CH_T || kind == CH_P)) || (l == LNU_ && kind == CH_N) || (l == LMNU_ && kind == CH_M);
@@ -813,7 +813,10 @@ __device__ __forceinline__ void lane_setup(const DevCosmo& c, const SolveParams&
   else if (ln.lane == c.nq + 1) { ln.kind = CH_P; ln.rbase = p.L + 1; ln.rstride = 1; ln.len = p.L + 1; }
   else if (ln.lane == c.nq + 2) { ln.kind = CH_N; ln.rbase = 2 * (p.L + 1); ln.rstride = 1; ln.len = p.Lnu + 1; }
   else { ln.kind = CH_IDLE; ln.rbase = 0; ln.rstride = 0; ln.len = 0; }
-  if constexpr (TR::MAXLEN > 0) { ln.base = ln.lane; ln.stride = TR::NCH; ln.iS = TR::MAXLEN * TR::NCH; }
+  if constexpr (TR::MAXLEN > 0) {
+    const bool own = (TR::NCH == 32) || ln.kind != CH_IDLE;     // compact layout: idle lanes own no column
+    ln.base = own ? ln.lane : 0; ln.stride = own ? TR::NCH : 0; ln.iS = TR::MAXLEN * TR::NCH;
+  }
   else { ln.base = ln.rbase; ln.stride = ln.rstride; ln.iS = ln.riS; }
 }
 
