@@ -41,6 +41,10 @@ struct bolt_cosmo {
   double* d_tables = nullptr;
   double* d_dtables = nullptr;         // partial tables [NTABLES][np][n_x+2] (nd > 1)
   const DevCosmo** d_list = nullptr;   // device array {d}: the 1-cosmology work list of K1
+  // K1 view of the partials: parameters that never reach the hierarchy (A, n: they enter through the primordial weight of
+  // K2 only) have identically zero sensitivities and are not carried through the ODE solve
+  DevCosmo* d_k1 = nullptr; const DevCosmo** d_list_k1 = nullptr; double* d_dtables_k1 = nullptr;
+  int np_k1 = 0; int map_k1[MAX_NP] = {0};
 };
 
 // DFMA throughput microbenchmark: 8 independent FMA chains per thread (the FP64 roofline denominator;
@@ -186,7 +190,7 @@ int launch_k1_dual_reg(bolt_ctx* ctx, const SolveParams& p) {
 
 // Launch K1 on device buffers.  cos_list: device array of ncos cosmology pointers; work item g (0 <= g < nk) belongs to
 // cosmology g / nk_per.
-int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int np, int nk_per, const double* d_k, const int* d_order, int nk,
+int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int np, int out_nd, const int* comp_map, int nk_per, const double* d_k, const int* d_order, int nk,
                      const bolt_opts* o, double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status,
                      long long* d_nsteps, long long* d_nreject) {
   SolveParams p;
@@ -198,6 +202,8 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   p.S_T = d_ST; p.S_P = d_SP; p.u_hist = d_hist; p.u_final = d_final;
   p.status = d_status; p.nsteps = d_nsteps; p.nreject = d_nreject; p.counter = ctx->d_counter;
   p.dbg = ctx->d_dbg; p.dbg_cap = ctx->d_dbg ? DBG_CAP : 0;
+  p.out_nd = out_nd;
+  for (int j = 0; j < MAX_NP; j++) p.comp_map[j] = (comp_map && j < np) ? comp_map[j] : 1 + j;
   if (np > 0) {     // value + gradient in one pass
     if (!getenv("BOLT_K1_GENERIC") && nq == 15 && p.L == 8 && p.Lnu == 8 && p.Lm == 10) {     // register-resident (hierarchy_dual_reg.cuh)
       typedef Trunc<8, 8, 10, 15, 18> TRD;
@@ -227,7 +233,8 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
 int launch_hierarchy(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, const int* d_order, int nk, const bolt_opts* o,
                      double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status, long long* d_nsteps,
                      long long* d_nreject) {
-  return launch_hierarchy(ctx, c->d_list, c->h.nq, c->h.np, nk, d_k, d_order, nk, o, d_ST, d_SP, d_hist, d_final, d_status, d_nsteps, d_nreject);
+  const bool compact = c->d_list_k1 != nullptr;
+  return launch_hierarchy(ctx, compact ? c->d_list_k1 : c->d_list, c->h.nq, c->np_k1, c->h.nd, c->map_k1, nk, d_k, d_order, nk, o, d_ST, d_SP, d_hist, d_final, d_status, d_nsteps, d_nreject);
 }
 
 int upload_k_sorted(bolt_ctx* ctx, const double* k, int nk, DevBuf<double>& d_k, DevBuf<int>& d_order) {
@@ -526,6 +533,48 @@ int bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* d, bolt_cosmo** out)
   cudaMemcpy(c->d, &h, sizeof(DevCosmo), cudaMemcpyHostToDevice);
   eta_end_kernel<<<1, 1, 0, ctx->stream>>>(c->d);
   cudaStreamSynchronize(ctx->stream);
+  // compact K1 view: keep only the partials with a non-zero table or (K1-relevant) scalar partial
+  c->np_k1 = 0;
+  if (h.np > 0) {
+    const int np = h.np;
+    for (int j = 0; j < np; j++) {
+      bool active = false;
+      for (int i = 0; i < BOLT_NSCALARS && !active; i++) if (i != BOLT_S_A && i != BOLT_S_n && h.ds[i][j] != 0.0) active = true;
+      for (size_t i = 0; i < (size_t)BOLT_NTABLES * nc && !active; i++) if (d->tables[i * nd + 1 + j] != 0.0) active = true;
+      if (active) c->map_k1[c->np_k1++] = 1 + j;
+    }
+    static const int supported[] = {0, 1, 2, 3, 4, 6};
+    bool ok = false; for (int v : supported) ok |= (v == c->np_k1);
+    if (c->np_k1 < np && ok) {
+      DevCosmo k1 = h;
+      k1.np = c->np_k1; k1.nd = 1 + c->np_k1;
+      const int na = c->np_k1;
+      if (na > 0) {
+        std::vector<double> dt((size_t)BOLT_NTABLES * na * nc);
+        for (int t = 0; t < BOLT_NTABLES; t++)
+          for (int a = 0; a < na; a++)
+            for (int i = 0; i < nc; i++) dt[((size_t)t * na + a) * nc + i] = d->tables[((size_t)t * nc + i) * nd + c->map_k1[a]];
+        cudaMalloc(&c->d_dtables_k1, dt.size() * sizeof(double));
+        cudaMemcpy(c->d_dtables_k1, dt.data(), dt.size() * sizeof(double), cudaMemcpyHostToDevice);
+        for (int t = 0; t < BOLT_NTABLES; t++) k1.dtab[t] = c->d_dtables_k1 + (size_t)t * na * nc;
+        for (int a = 0; a < na; a++) {
+          const int j = c->map_k1[a] - 1;
+          for (int i = 0; i < BOLT_NSCALARS; i++) k1.ds[i][a] = h.ds[i][j];
+          for (int i = 0; i < h.nq; i++) { k1.dq[i][a] = h.dq[i][j]; k1.dwq[i][a] = h.dwq[i][j]; }
+          k1.dOmega_nu[a] = h.dOmega_nu[j]; k1.deta_end[a] = h.deta_end[j];
+        }
+      }
+      cudaMalloc(&c->d_k1, sizeof(DevCosmo));
+      cudaMemcpy(c->d_k1, &k1, sizeof(DevCosmo), cudaMemcpyHostToDevice);
+      eta_end_kernel<<<1, 1, 0, ctx->stream>>>(c->d_k1);
+      cudaStreamSynchronize(ctx->stream);
+      cudaMalloc(&c->d_list_k1, sizeof(DevCosmo*));
+      cudaMemcpy(c->d_list_k1, &c->d_k1, sizeof(DevCosmo*), cudaMemcpyHostToDevice);
+    } else {
+      c->np_k1 = np;
+      for (int j = 0; j < np; j++) c->map_k1[j] = 1 + j;
+    }
+  }
   if (cudaMalloc(&c->d_list, sizeof(DevCosmo*)) != cudaSuccess) { cudaFree(c->d); cudaFree(c->d_tables); delete c; return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc list"); }
   cudaMemcpy(c->d_list, &c->d, sizeof(DevCosmo*), cudaMemcpyHostToDevice);
   *out = c;
@@ -536,6 +585,7 @@ int bolt_cosmo_free(bolt_ctx* ctx, bolt_cosmo* c) {
   if (!c) return BOLT_OK;
   if (ctx) cudaSetDevice(ctx->device);
   cudaFree(c->d); cudaFree(c->d_tables); cudaFree(c->d_dtables); cudaFree(c->d_list);
+  cudaFree(c->d_k1); cudaFree(c->d_list_k1); cudaFree(c->d_dtables_k1);
   delete c;
   return BOLT_OK;
 }
@@ -556,7 +606,7 @@ int bolt_solve(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, cons
   if (S_T) { CUDA_OK(d_ST.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemsetAsync(d_ST.p, 0, d_ST.n * 8, ctx->stream)); }
   if (S_P) { CUDA_OK(d_SP.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(cudaMemsetAsync(d_SP.p, 0, d_SP.n * 8, ctx->stream)); }
   if (u_hist) { CUDA_OK(d_hist.alloc(ctx, (size_t)nk * n_x * n)); CUDA_OK(cudaMemsetAsync(d_hist.p, 0, d_hist.n * 8, ctx->stream)); }
-  if (u_final) CUDA_OK(d_final.alloc(ctx, (size_t)nk * n * c->h.nd));
+  if (u_final) { CUDA_OK(d_final.alloc(ctx, (size_t)nk * n * c->h.nd)); CUDA_OK(cudaMemsetAsync(d_final.p, 0, d_final.n * 8, ctx->stream)); }
   CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk)); CUDA_OK(d_nr.alloc(ctx, nk));
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, o, d_ST.p, d_SP.p, d_hist.p, d_final.p, d_status.p, d_ns.p, d_nr.p);
   if (rc) return rc;
@@ -622,6 +672,9 @@ int bolt_spectra(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, co
   DevBuf<double> d_k, d_ST, d_SP, d_cl; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns;
   rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
   CUDA_OK(d_ST.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(d_SP.alloc(ctx, (size_t)nk * n_x));
+  if (c->np_k1 < c->h.np) {     // partials the hierarchy does not carry (A, n) stay exactly zero in the source grids
+    CUDA_OK(cudaMemsetAsync(d_ST.p, 0, d_ST.n * 8, ctx->stream)); CUDA_OK(cudaMemsetAsync(d_SP.p, 0, d_SP.n * 8, ctx->stream));
+  }
   CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk)); CUDA_OK(d_cl.alloc(ctx, 3 * ncl));
   bolt_opts oo = *o;
   oo.ix_first = std::max(oo.ix_first, ix_start);    // the LOS sum only reads rows >= ix_start (spectra.jl:86)
@@ -656,6 +709,7 @@ int bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const
   DevBuf<double> d_k, d_final, d_pk; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns;
   rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
   CUDA_OK(d_final.alloc(ctx, (size_t)nk * n * nd)); CUDA_OK(d_pk.alloc(ctx, (size_t)nk * nd));
+  if (c->np_k1 < c->h.np) CUDA_OK(cudaMemsetAsync(d_final.p, 0, d_final.n * 8, ctx->stream));
   CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk));
   bolt_opts oo = *o; oo.ix_first = c->h.n_x;   // plin only needs perturb(0): no source sampling
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, nullptr, nullptr, nullptr, d_final.p, d_status.p, d_ns.p, nullptr);

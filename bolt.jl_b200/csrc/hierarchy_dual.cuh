@@ -411,12 +411,12 @@ __device__ __forceinline__ void sample_sources_d(const DevCosmo& c, const Lane& 
   if (ln.lane == 0) {
     const T sT = term1 + term2 + term3;
     const T sP = (3.0 / (4.0 * y * y)) * g * Pi;
-    if (p.S_T) { double* o = p.S_T + ((size_t)ik * c.n_x + ix) * ND; o[0] = sT.v;
+    if (p.S_T) { double* o = p.S_T + ((size_t)ik * c.n_x + ix) * p.out_nd; o[0] = sT.v;
 #pragma unroll
-      for (int j = 0; j < NP; j++) o[1 + j] = sT.d[j]; }
-    if (p.S_P) { double* o = p.S_P + ((size_t)ik * c.n_x + ix) * ND; o[0] = sP.v;
+      for (int j = 0; j < NP; j++) o[p.comp_map[j]] = sT.d[j]; }
+    if (p.S_P) { double* o = p.S_P + ((size_t)ik * c.n_x + ix) * p.out_nd; o[0] = sP.v;
 #pragma unroll
-      for (int j = 0; j < NP; j++) o[1 + j] = sP.d[j]; }
+      for (int j = 0; j < NP; j++) o[p.comp_map[j]] = sP.d[j]; }
   }
 }
 
@@ -694,11 +694,11 @@ __global__ void __launch_bounds__(32) hierarchy_dual_kernel(SolveParams p) {
     }
     if (rsa_flag && status == BOLT_K_OK) status = BOLT_K_RSA_TRIGGERED;
     if (p.u_final) {   // [nk][n][nd]
-      double* out = p.u_final + (size_t)ik * n * ND;
+      double* out = p.u_final + (size_t)ik * n * p.out_nd;
 #pragma unroll 1
       for (int l = 0; l < ln.len; l++)
-        for (int j = 0; j < ND; j++) out[(size_t)(ln.rbase + l * ln.rstride) * ND + j] = U.p[(size_t)j * n + ln.base + l * ln.stride];
-      if (ln.lane < 5) for (int j = 0; j < ND; j++) out[(size_t)(ln.riS + ln.lane) * ND + j] = U.p[(size_t)j * n + ln.iS + ln.lane];
+        for (int j = 0; j < ND; j++) out[(size_t)(ln.rbase + l * ln.rstride) * p.out_nd + (j ? p.comp_map[j - 1] : 0)] = U.p[(size_t)j * n + ln.base + l * ln.stride];
+      if (ln.lane < 5) for (int j = 0; j < ND; j++) out[(size_t)(ln.riS + ln.lane) * p.out_nd + (j ? p.comp_map[j - 1] : 0)] = U.p[(size_t)j * n + ln.iS + ln.lane];
     }
     if (ln.lane == 0) {
       if (p.status) p.status[ik] = status;

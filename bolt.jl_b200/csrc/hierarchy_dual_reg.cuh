@@ -318,11 +318,11 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
     }
     if (rsa_flag && status == BOLT_K_OK) status = BOLT_K_RSA_TRIGGERED;
     if (p.u_final) {   // [nk][n][nd]
-      double* out = p.u_final + (size_t)ik * n * ND;
+      double* out = p.u_final + (size_t)ik * n * p.out_nd;
 #pragma unroll 1
       for (int l = 0; l < ln.len; l++)
-        for (int j = 0; j < ND; j++) out[(size_t)(ln.rbase + l * ln.rstride) * ND + j] = U.p[(size_t)j * na + ln.base + l * ln.stride];
-      if (ln.lane < 5) for (int j = 0; j < ND; j++) out[(size_t)(ln.riS + ln.lane) * ND + j] = U.p[(size_t)j * na + ln.iS + ln.lane];
+        for (int j = 0; j < ND; j++) out[(size_t)(ln.rbase + l * ln.rstride) * p.out_nd + (j ? p.comp_map[j - 1] : 0)] = U.p[(size_t)j * na + ln.base + l * ln.stride];
+      if (ln.lane < 5) for (int j = 0; j < ND; j++) out[(size_t)(ln.riS + ln.lane) * p.out_nd + (j ? p.comp_map[j - 1] : 0)] = U.p[(size_t)j * na + ln.iS + ln.lane];
     }
     if (ln.lane == 0) {
       if (p.status) p.status[ik] = status;

@@ -45,6 +45,8 @@ struct SolveParams {
   long long* nsteps;      // [nk]
   long long* nreject;     // [nk]
   int* counter;           // work queue head
+  int out_nd;             // doubles per output element of S_T, S_P, u_final (1 + number of partials the CALLER carries)
+  int comp_map[MAX_NP];   // dual kernels: output slot (1-based partial index) of the kernel's partial j
   double* dbg;            // optional step log of mode 0: [dbg_cap][4] = x, dt, EEst, accepted
   int dbg_cap;
 };
@@ -573,8 +575,8 @@ __device__ __forceinline__ void sample_sources(const DevCosmo& c, const Lane& ln
                                                 + Hx * Hx * (gpp * Pi + 2.0 * gp * dPi + g * ddPi));            // :379-381
   const double y = k * (c.eta_end - b.eta);                                                                    // :401
   if (ln.lane == 0) {
-    if (p.S_T) p.S_T[(size_t)ik * c.n_x + ix] = term1 + term2 + term3;
-    if (p.S_P) p.S_P[(size_t)ik * c.n_x + ix] = (3.0 / (4.0 * y * y)) * g * Pi;                                 // :403
+    if (p.S_T) p.S_T[((size_t)ik * c.n_x + ix) * p.out_nd] = term1 + term2 + term3;
+    if (p.S_P) p.S_P[((size_t)ik * c.n_x + ix) * p.out_nd] = (3.0 / (4.0 * y * y)) * g * Pi;                                 // :403
   }
 }
 
@@ -1100,10 +1102,10 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
     }
     if (rsa_flag && status == BOLT_K_OK) status = BOLT_K_RSA_TRIGGERED;
     if (p.u_final) {
-      double* out = p.u_final + (size_t)ik * n;
-      #pragma unroll 1
-      for (int l = 0; l < ln.len; l++) out[ln.rbase + l * ln.rstride] = U[ln.base + l * ln.stride];
-      if (ln.lane < 5) out[ln.riS + ln.lane] = U[ln.iS + ln.lane];
+      double* out = p.u_final + (size_t)ik * n * p.out_nd;
+#pragma unroll 1
+      for (int l = 0; l < ln.len; l++) out[(size_t)(ln.rbase + l * ln.rstride) * p.out_nd] = U[ln.base + l * ln.stride];
+      if (ln.lane < 5) out[(size_t)(ln.riS + ln.lane) * p.out_nd] = U[ln.iS + ln.lane];
     }
     if (ln.lane == 0) {
       if (p.status) p.status[ik] = status;

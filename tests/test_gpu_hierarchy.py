@@ -125,6 +125,7 @@ def test_unsupported_partial_count_fails_loudly(cosmo, gpu_ctx):
     hc = cosmo.hc
     sc = np.zeros((abi.NSCALARS, 6)); tb = np.zeros(hc.tables.shape[:2] + (6,))
     sc[:, 0] = hc.scalars[:, 0]; tb[..., 0] = hc.tables[..., 0]
+    tb[..., 1:] = 1e-3 * hc.tables[..., :1]           # five non-trivial partials (all-zero partials would simply not be carried)
     dc = capi.DeviceCosmo(gpu_ctx, abi.HostCosmo(sc, hc.quad_pts, hc.quad_wts, tb, hc.x0, hc.dx))
     with pytest.raises(capi.BoltError, match="partials"):
         dc.solve(np.array([10.0]) * cosmo.bg.H0, abi.make_opts(8, 8, 10, fixed_dt=0.05), want=("S_T",))
