@@ -138,6 +138,20 @@ def gradient_arm(ctx, ells):
                     "partials); error control runs over value and partials like the reference, hence more steps than value-only"}
 
 
+def plin_arm(ctx, hcosmo, dc):
+    """BASELINE configs[1]: linear matter P(k) via plin with massive neutrinos, 500 log-spaced k-modes, the reference's plin
+    defaults l_gamma = l_nu = 50, l_mnu = 20 (state n = 473), reltol 1e-5 (src/spectra.jl:163-164).  Generic K1 path."""
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    bg = hcosmo["bg"]
+    ks = B.log10_k(10 * bg.H0, 5000 * bg.H0, 500)
+    o = abi.make_opts(50, 50, 20, reltol=1e-5, abstol=1e-6)
+    for rep in range(2):
+        t0 = time.perf_counter(); pk, st, ns = dc.plin(ks, o); dt = time.perf_counter() - t0
+    return {"workload": "plin, 500 log10_k modes (10 H0 .. 5000 H0), n = 473, reltol 1e-5", "ms": 1e3 * dt, "kmode_solves_per_s": len(ks) / dt,
+            "hierarchy_ms": ctx.timing()["hierarchy_ms"], "ode_steps_per_solve": float(ns.mean()), "failed_modes": int((st != 0).sum())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -281,6 +295,8 @@ def main():
             line["cpu_baseline"] = cb
         if not args.no_gradients and world == 1:
             line["gradients"] = gradient_arm(ctx, ells)
+        if world == 1:
+            line["plin"] = plin_arm(ctx, hcos[0], dcs[0])
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
