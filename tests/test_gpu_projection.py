@@ -91,3 +91,46 @@ def test_plin_matches_oracle(cosmo, oracle, dev):
     rk, rst, rns = oracle.plin(ks, o)
     assert np.all(st == 0) and np.all(pk > 0)
     assert np.abs(pk / rk - 1).max() < 1e-4
+
+
+def test_full_size_c3_properties(cosmo, dev):
+    """BASELINE config 3 at full size (2000 quadratic k-modes, ℓ = 2..2500): size-independent properties.
+    The oracle would need hours here; parity at this size is carried by determinism, the Cauchy-Schwarz bound of the
+    discrete k-sum, invariance under the choice of multipole subset, and agreement with the 100-mode golden spectrum."""
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    bg = cosmo.bg
+    ks = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 2000)
+    ells = np.arange(2, 2501, dtype=np.int32)
+    o = abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6)
+    args = (0.01 * bg.H0, 1000 * bg.H0, 5000, cosmo.ix_start)
+    tt, te, ee, st, ns = dev.spectra(ks, o, ells, *args)
+    assert np.all(st == 0) and ns.min() > 100 and ns.max() < 5000
+    assert np.all(np.isfinite(tt)) and np.all(tt > 0) and np.all(ee > 0)
+    assert np.all(te ** 2 <= tt * ee * (1 + 1e-12))
+    tt2, te2, ee2, _, ns2 = dev.spectra(ks, o, ells, *args)
+    assert np.array_equal(tt, tt2) and np.array_equal(te, te2) and np.array_equal(ee, ee2) and np.array_equal(ns, ns2)   # bitwise
+    sub = ells[7::97]
+    stt, ste, see, _, _ = dev.spectra(ks, o, sub, *args)
+    assert np.allclose(stt, tt[7::97], rtol=1e-13) and np.allclose(see, ee[7::97], rtol=1e-13)
+    # the acoustic peaks are where they should be and the 100-mode spectrum is within its own k-interpolation error
+    g = load_golden("oracle_c1.npz")
+    sel = np.searchsorted(ells, g["ell"])
+    assert np.abs(tt[sel] / g["tt"] - 1)[3:].max() < 0.08
+    dl = ells * (ells + 1) * tt
+    assert 180 <= ells[np.argmax(dl[:400])] <= 260
+
+
+def test_c4_style_high_lgamma(cosmo, dev):
+    """BASELINE config 4 in miniature: ℓᵧ = 50 through source_grid's interface (state n = 281, generic kernel path).
+    Raising the photon truncation must not move the spectrum by more than the truncation error of ℓᵧ = 8."""
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    bg = cosmo.bg
+    ks = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 150)
+    ells = np.array([10, 100, 220, 540, 800, 1500], dtype=np.int32)
+    args = (0.01 * bg.H0, 1000 * bg.H0, 5000, cosmo.ix_start)
+    lo = dev.spectra(ks, abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6), ells, *args)
+    hi = dev.spectra(ks, abi.make_opts(50, 8, 10, reltol=1e-11, abstol=1e-6), ells, *args)
+    assert np.all(hi[3] == 0) and abi.state_dim(50, 8, 10, 15) == 281
+    assert np.abs(hi[0] / lo[0] - 1).max() < 0.03 and np.abs(hi[2] / lo[2] - 1).max() < 0.06
