@@ -172,15 +172,17 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
         };
         const double xs = x + KC_C[s] * dt;
         // ---- value: W U = r in registers ----
+        // every right-hand side is formed ONCE and parked in the stage's own (not yet written) z slot, so that
+        // z = (solution - rhs)/gamma needs neither a register copy nor a second pass over the six state arrays
 #pragma unroll
-        for (int l = 0; l < MAXLEN; l++) rr[l] = live ? rhs_at(0, lo_ + l * NCH) : 0.0;
+        for (int l = 0; l < MAXLEN; l++) { double v = 0.0; if (live) { const int idx = lo_ + l * NCH; v = rhs_at(0, idx); zout.p[idx] = v; } rr[l] = v; }
 #pragma unroll
-        for (int j = 0; j < 5; j++) r5[j] = rhs_at(0, ln.iS + j);
+        for (int j = 0; j < 5; j++) { const int idx = ln.iS + j; const double v = rhs_at(0, idx); r5[j] = v; zout.p[idx] = v; }
         eval_bg_fast(c, ln, mc, xs, bf);
         rsa_flag |= (ln.k * bf.eta > 240.0) && (-bf.taup * bf.H > 100.0 * bf.eta);
         factor_reg<TR>(ln, bf, h, f);
         solve_reg<TR>(ln, bf, f, rr, r5);          // rr, r5 = stage value U
-        // ---- G = (dA/dp) U in dual arithmetic on the plain stage value; system right-hand sides r_j + h G_j -> zout_j ----
+        // ---- G = (dA/dp) U in dual arithmetic on the plain stage value; h G_j -> zout_j ----
         eval_bg_d<NP>(c, ln, xs, bd);
         {
           MetricG<NP> m;
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
             if (live) {
               const int idx = lo_ + l * NCH;
 #pragma unroll
-              for (int j = 0; j < NP; j++) zout.p[(size_t)(1 + j) * na + idx] = rhs_at(1 + j, idx) + h * g.d[j];
+              for (int j = 0; j < NP; j++) zout.p[(size_t)(1 + j) * na + idx] = h * g.d[j];
             }
           }
           const T g0 = m.dPhi, g1 = bd.kappa * m.v - 3.0 * m.dPhi, g2 = -(bd.kappa * m.Psi) - m.v, g3 = bd.kappa * m.v_b - 3.0 * m.dPhi;
@@ -206,28 +208,42 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
 #pragma unroll
           for (int j = 0; j < NP; j++) {      // every lane stores the same scalars (see the value kernel)
             double* zp = zout.p + (size_t)(1 + j) * na + ln.iS;
-            zp[0] = rhs_at(1 + j, ln.iS) + h * g0.d[j]; zp[1] = rhs_at(1 + j, ln.iS + 1) + h * g1.d[j]; zp[2] = rhs_at(1 + j, ln.iS + 2) + h * g2.d[j];
-            zp[3] = rhs_at(1 + j, ln.iS + 3) + h * g3.d[j]; zp[4] = rhs_at(1 + j, ln.iS + 4) + h * g4.d[j];
+            zp[0] = h * g0.d[j]; zp[1] = h * g1.d[j]; zp[2] = h * g2.d[j]; zp[3] = h * g3.d[j]; zp[4] = h * g4.d[j];
           }
         }
         // value stage increment (U is still in rr / r5)
 #pragma unroll
-        for (int l = 0; l < MAXLEN; l++) if (live) { const int idx = lo_ + l * NCH; zout.p[idx] = (rr[l] - rhs_at(0, idx)) * (1.0 / KC_GAMMA); }
+        for (int l = 0; l < MAXLEN; l++) if (live) { const int idx = lo_ + l * NCH; zout.p[idx] = (rr[l] - zout.p[idx]) * (1.0 / KC_GAMMA); }
+        {
+          double zz[5];
 #pragma unroll
-        for (int j = 0; j < 5; j++) { const int idx = ln.iS + j; zout.p[idx] = (r5[j] - rhs_at(0, idx)) * (1.0 / KC_GAMMA); }
+          for (int j = 0; j < 5; j++) zz[j] = (r5[j] - zout.p[ln.iS + j]) * (1.0 / KC_GAMMA);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 5; j++) zout.p[ln.iS + j] = zz[j];
+        }
         // ---- partials: W S_j = r_j + h G_j with the factorisation in hand ----
 #pragma unroll 1
         for (int j = 1; j <= NP; j++) {
           double* zj = zout.p + (size_t)j * na;
+          // system right-hand side r_j + h G_j (h G_j waits in zj); r_j is parked in zj for the stage increment
 #pragma unroll
-          for (int l = 0; l < MAXLEN; l++) rr[l] = live ? zj[lo_ + l * NCH] : 0.0;
+          for (int l = 0; l < MAXLEN; l++) { double v = 0.0; if (live) { const int idx = lo_ + l * NCH; const double rj = rhs_at(j, idx); v = rj + zj[idx]; zj[idx] = rj; } rr[l] = v; }
+          // (the five scalars are shared by all lanes: every lane reads, the warp converges, then every lane writes the same value)
+          double rj5[5];
 #pragma unroll
-          for (int q = 0; q < 5; q++) r5[q] = zj[ln.iS + q];
+          for (int q = 0; q < 5; q++) { const int idx = ln.iS + q; rj5[q] = rhs_at(j, idx); r5[q] = rj5[q] + zj[idx]; }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 5; q++) zj[ln.iS + q] = rj5[q];
           solve_reg<TR>(ln, bf, f, rr, r5);
 #pragma unroll
-          for (int l = 0; l < MAXLEN; l++) if (live) { const int idx = lo_ + l * NCH; zj[idx] = (rr[l] - rhs_at(j, idx)) * (1.0 / KC_GAMMA); }
+          for (int l = 0; l < MAXLEN; l++) if (live) { const int idx = lo_ + l * NCH; zj[idx] = (rr[l] - zj[idx]) * (1.0 / KC_GAMMA); }
 #pragma unroll
-          for (int q = 0; q < 5; q++) { const int idx = ln.iS + q; zj[idx] = (r5[q] - rhs_at(j, idx)) * (1.0 / KC_GAMMA); }
+          for (int q = 0; q < 5; q++) rj5[q] = (r5[q] - zj[ln.iS + q]) * (1.0 / KC_GAMMA);
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 5; q++) zj[ln.iS + q] = rj5[q];
         }
       }
       // u_{n+1} for every component (z2 slot)
