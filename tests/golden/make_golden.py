@@ -29,6 +29,11 @@ def reference_fixtures():
         out[f"x_{tag}"] = c[0, sel]; out[f"k_{tag}"] = c[1, 0]
         out[f"d_b_{tag}"] = c[3, sel]; out[f"phi_{tag}"] = c[7, sel]
     np.savez_compressed(f"{HERE}/class_px.npz", **out)
+    # massive-neutrino run with reionization (16 rows: ..., d_ncdm[0] at row 6, phi at row 8); consumed only by
+    # scripts/plot_perts_x.jl in the reference: an extra pin for the massive-neutrino hierarchy and rho_sigma
+    c = np.loadtxt(f"{REF}/class_px_kp03_nofluid_re.dat")
+    sel = np.arange(0, c.shape[1], 6)
+    np.savez_compressed(f"{HERE}/class_px_mnu.npz", x=c[0, sel], k=c[1, 0], d_b=c[3, sel], d_cdm=c[4, sel], d_ncdm=c[6, sel], phi=c[8, sel])
     camb = np.loadtxt(f"{REF}/camb_rough_ttteee_unlensed.dat")
     ells = np.arange(10, 2501, 10)
     np.savez_compressed(f"{HERE}/camb_cl.npz", ell=ells, tt=np.interp(ells, camb[0], camb[1]),

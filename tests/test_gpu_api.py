@@ -71,6 +71,16 @@ def test_class_potential_at_all_fixture_wavenumbers(cosmo_nonu):
         assert err < 2e-3, (t, err)
 
 
+def test_class_massive_neutrino_pin(cosmo, dev):
+    """The massive-neutrino CLASS fixture (see tests/test_oracle.py) through the device."""
+    from bolt_b200 import abi
+    from test_oracle import _mnu_check
+    g = load_golden("class_px_mnu.npz")
+    out = dev.solve(np.array([cosmo.par.h * float(g["k"])]), abi.make_opts(50, 50, 20, reltol=1e-8, abstol=1e-8), want=("u_hist",))
+    assert out["status"][0] == 0
+    _mnu_check(cosmo, out["u_hist"][0])
+
+
 def test_plin_scalar_and_vector(cosmo):
     """examples/basic_usage.jl:11-14: pL = [plin(k, 𝕡, bg, ih) for k in ks]."""
     import bolt_b200 as B

@@ -27,6 +27,36 @@ def test_oracle_vs_class_phi_deltab(cosmo_nonu):
     assert np.all(np.abs(-d_b / g["d_b_p03"][::-1] - 1) < 1e-3)
 
 
+def _mnu_check(cosmo, uh):
+    """Φ, δ_b, δ_cdm and the massive-neutrino density contrast against CLASS (ncdm, no fluid approximation, reionization)."""
+    from bolt_b200.host.background import q_grid, f0, dxdq
+    g = load_golden("class_px_mnu.npz")
+    par, bg = cosmo.par, cosmo.bg
+    xg = bg.x_grid; n = uh.shape[1]
+    cx = g["x"][::-1]; keep = cx > -12
+    def rel(mine, ref, sign=1.0):
+        return np.abs(sign * CubicSpline(xg, mine)(cx)[keep] / ref[::-1][keep] - 1).max()
+    assert rel(uh[:, n - 5], g["phi"]) < 1.5e-3
+    assert rel(uh[:, n - 2], g["d_b"], -1.0) < 1.5e-3
+    assert rel(uh[:, n - 4], g["d_cdm"], -1.0) < 1.5e-3
+    q, lqmi, lqma = q_grid(par, bg.quad_pts); w = f0(q, par) / dxdq(q, lqmi, lqma) * bg.quad_wts
+    eps = np.sqrt(q ** 2 + (np.exp(xg)[:, None] * par.Σm_ν) ** 2)
+    iM = 2 * 51 + 51
+    rho = 4 * np.pi * np.sum(q ** 2 * eps * w * uh[:, iM:iM + 15], axis=1)       # ρ_σ (perturbations.jl:127-145)
+    d_ncdm = rho / bg.ρ0M(xg) * np.exp(-4 * xg)                                     # scripts/plot_perts_x.jl:70
+    assert rel(d_ncdm, g["d_ncdm"], -1.0) < 3e-2
+
+
+def test_oracle_vs_class_massive_neutrinos(cosmo, oracle):
+    """Extra pin (no reference test consumes it; scripts/plot_perts_x.jl plots it): default CosmoParams (Σm_ν = 0.06 eV),
+    k = 0.03 h/Mpc, ℓᵧ = ℓ_ν = 50, ℓ_mν = 20, reltol 1e-8."""
+    from bolt_b200 import abi
+    g = load_golden("class_px_mnu.npz")
+    out = oracle.solve(np.array([cosmo.par.h * float(g["k"])]), abi.make_opts(50, 50, 20, reltol=1e-8, abstol=1e-8), want=("u_hist",))
+    assert out["status"][0] == 0
+    _mnu_check(cosmo, out["u_hist"][0])
+
+
 def test_oracle_cl_vs_camb(cosmo, oracle):
     """test/runtests.jl:149-185: D_ℓ^TT, D_ℓ^EE within 11 % of CAMB for ℓ = 10:10:2500 (100 quadratic k-modes).
     The source grids are the committed oracle outputs (tests/golden/make_golden.py); the projection is re-run."""
