@@ -34,6 +34,9 @@ def reference_fixtures():
     c = np.loadtxt(f"{REF}/class_px_kp03_nofluid_re.dat")
     sel = np.arange(0, c.shape[1], 6)
     np.savez_compressed(f"{HERE}/class_px_mnu.npz", x=c[0, sel], k=c[1, 0], d_b=c[3, sel], d_cdm=c[4, sel], d_ncdm=c[6, sel], phi=c[8, sel])
+    pk = np.loadtxt(f"{REF}/camb_pk_x0.dat")                  # k [h/Mpc], P(k) [(Mpc/h)^3] at z = 0; no reference test consumes it
+    sel = np.arange(0, pk.shape[1], 20)
+    np.savez_compressed(f"{HERE}/camb_pk.npz", k_h=pk[0, sel], pk_h3=pk[1, sel])
     camb = np.loadtxt(f"{REF}/camb_rough_ttteee_unlensed.dat")
     ells = np.arange(10, 2501, 10)
     np.savez_compressed(f"{HERE}/camb_cl.npz", ell=ells, tt=np.interp(ells, camb[0], camb[1]),

@@ -81,6 +81,15 @@ def test_class_massive_neutrino_pin(cosmo, dev):
     _mnu_check(cosmo, out["u_hist"][0])
 
 
+def test_plin_vs_camb_matter_power(cosmo):
+    """P(k) at z = 0 against CAMB over two decades in k (extra pin, see tests/test_oracle.py)."""
+    import bolt_b200 as B
+    from test_oracle import camb_pk_at
+    kh = np.geomspace(2e-3, 0.3, 24)
+    pk = B.plin(kh * cosmo.par.h, cosmo.par, cosmo.bg, cosmo.ih)
+    assert np.abs(pk * cosmo.par.h ** 3 / camb_pk_at(kh) - 1).max() < 5e-3
+
+
 def test_plin_scalar_and_vector(cosmo):
     """examples/basic_usage.jl:11-14: pL = [plin(k, 𝕡, bg, ih) for k in ks]."""
     import bolt_b200 as B

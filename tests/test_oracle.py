@@ -57,6 +57,21 @@ def test_oracle_vs_class_massive_neutrinos(cosmo, oracle):
     _mnu_check(cosmo, out["u_hist"][0])
 
 
+def camb_pk_at(kh):
+    g = load_golden("camb_pk.npz")
+    return np.exp(np.interp(np.log(kh), np.log(g["k_h"]), np.log(g["pk_h3"])))
+
+
+def test_oracle_plin_vs_camb(cosmo, oracle):
+    """Extra pin: the reference has no automated test of plin; its data directory holds CAMB's z = 0 matter power
+    spectrum (scripts/first_plin.jl plots the ratio).  plin defaults (ℓᵧ = ℓ_ν = 50, ℓ_mν = 20, reltol 1e-5), P in (Mpc/h)³."""
+    from bolt_b200 import abi
+    kh = np.array([0.01, 0.05, 0.2])
+    pk, st, _ = oracle.plin(kh * cosmo.par.h, abi.make_opts(50, 50, 20, reltol=1e-5, abstol=1e-6))
+    assert np.all(st == 0)
+    assert np.abs(pk * cosmo.par.h ** 3 / camb_pk_at(kh) - 1).max() < 5e-3
+
+
 def test_oracle_cl_vs_camb(cosmo, oracle):
     """test/runtests.jl:149-185: D_ℓ^TT, D_ℓ^EE within 11 % of CAMB for ℓ = 10:10:2500 (100 quadratic k-modes).
     The source grids are the committed oracle outputs (tests/golden/make_golden.py); the projection is re-run."""
