@@ -10,6 +10,9 @@
 #include <string>
 #include <vector>
 
+#ifndef K1_NCH
+#define K1_NCH 32
+#endif
 #include "hierarchy_kernel.cuh"
 #include "hierarchy_dual.cuh"
 #include "hierarchy_dual_reg.cuh"
@@ -133,7 +136,7 @@ int check_opts(bolt_ctx* ctx, const bolt_cosmo* c, const bolt_opts* o) {
 template <class TR>
 int launch_k1(bolt_ctx* ctx, const SolveParams& p) {
   auto kern = hierarchy_kernel_t<TR>;
-  const size_t smem = (size_t)k1_num_arrays<TR>() * k1_array_len<TR>(p.n) * sizeof(double);
+  const size_t smem = ((size_t)k1_num_arrays<TR>() * k1_array_len<TR>(p.n) + k1_extra_doubles<TR>()) * sizeof(double);
   CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int occ = 0;
@@ -225,8 +228,8 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   }
   const bool force_generic = getenv("BOLT_K1_GENERIC") != nullptr;     // development switch
   if (!force_generic && nq == 15 && p.Lnu == 8 && p.Lm == 10) {          // source_grid's truncations (src/spectra.jl:11)
-    if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15>>(ctx, p);         // l_gamma = 8: the reference default
-    if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15>>(ctx, p);       // l_gamma = 10: BASELINE config 1
+    if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15, K1_NCH>>(ctx, p);         // l_gamma = 8: the reference default
+    if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15, K1_NCH>>(ctx, p);       // l_gamma = 10: BASELINE config 1
   }
   return launch_k1<Trunc<0, 0, 0, 0>>(ctx, p);                            // any truncation (plin: 50, 50, 20)
 }

@@ -49,7 +49,7 @@ __device__ __forceinline__ Dual<NP> g_row_reg(const Lane& ln, const BgD<NP>& b, 
 }
 
 template <class TR, int NP> __host__ __device__ constexpr size_t k1_dualreg_smem_doubles() {
-  return (size_t)7 * (1 + NP) * (TR::MAXLEN * TR::NCH + 8);
+  return (size_t)7 * (1 + NP) * (TR::MAXLEN * TR::NCH + 8) + k1_extra_doubles<TR>();   // + factor scratch
 }
 
 template <class TR, int NP>
@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
       if (nsteps + nreject >= max_steps) { status = BOLT_K_MAXSTEPS; break; }
 
       RegFactor<TR> f;
+      f.fs = sm + (size_t)7 * (1 + NP) * (TR::MAXLEN * TR::NCH + 8) + ln.lane;
       BgS bf;
       double rr[MAXLEN], r5[5];
       bool accept = true; double EEst = 0.0, q11 = 0.0;

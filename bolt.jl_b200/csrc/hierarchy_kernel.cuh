@@ -645,12 +645,17 @@ __device__ __forceinline__ void eval_bg_fast(const DevCosmo& c, const Lane& ln, 
   } else { b.wPhi = mc.wPhi0 * ia2; b.wPsi = mc.wPsi0; }
 }
 
+// Factorisation state of one stage.  The inverse pivots and the beta vectors (23 doubles per lane) live in a lane-private
+// column of a shared-memory scratch (fs: row r of the lane at fs[r*FS_STRIDE]); only the border matrix and a few scalars stay
+// in registers.
 template <class TR>
 struct RegFactor {
-  double ibv[TR::MAXLEN > 0 ? TR::MAXLEN : 1];
-  double beta0[4], beta1[4], beta2[4];
+  double* fs;
   double M[4][4];
   double h, hk, hkap, vden, e4c, lo1, lo2;
+  static constexpr int FS_STRIDE = 32, FS_ROWS = (TR::MAXLEN > 0 ? TR::MAXLEN : 1) + 12;
+  __device__ __forceinline__ double& ibv(int l) const { return fs[l * FS_STRIDE]; }
+  __device__ __forceinline__ double& beta(int row, int j) const { return fs[(TR::MAXLEN + 4 * row + j) * FS_STRIDE]; }
 };
 
 // Solve M y = rhs by Gaussian elimination with partial pivoting on the augmented system (registers, select-based swaps).
@@ -701,7 +706,7 @@ __device__ __forceinline__ void factor_reg(const Lane& ln, const BgS& b, double 
     const double up = top ? 0.0 : f.hk * (1.0 - RLc(l));
     const double lo = top ? -f.hk : -f.hk * RLc(l);
     const double ibl = act ? fast_rcp(bd - (up * ibn) * lo_next) : 0.0;
-    f.ibv[l] = ibl; ibn = ibl; lo_next = act ? lo : 0.0;
+    f.ibv(l) = ibl; ibn = ibl; lo_next = act ? lo : 0.0;
   }
   const bool live = kind != CH_IDLE;
   const double up2 = f.hk * (1.0 - RLc(2)), up1 = f.hk * (1.0 - RLc(1)), up0 = f.hk;
@@ -711,31 +716,33 @@ __device__ __forceinline__ void factor_reg(const Lane& ln, const BgS& b, double 
   const double ib1 = live ? fast_rcp((1.0 + dtau) - m1 * lo2) : 0.0;
   const double m0 = up0 * ib1;
   const double ib0 = live ? fast_rcp((1.0 + (kind == CH_P ? dtau : 0.0)) - m0 * lo1) : 0.0;
-  f.ibv[2] = ib2; f.ibv[1] = ib1; f.ibv[0] = ib0; f.lo1 = lo1; f.lo2 = lo2;
+  f.ibv(2) = ib2; f.ibv(1) = ib1; f.ibv(0) = ib0; f.lo1 = lo1; f.lo2 = lo2;
   double C0[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0};
   if (kind == CH_M) { C0[0] = h * ln.df0; C1[1] = -f.hkap * (1.0 / 3.0) * b.eq * ln.df0; }
   else if (kind == CH_T) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); C1[3] = h * b.taup * (1.0 / 3.0); C2[2] = -h * b.taup * 0.1; }
   else if (kind == CH_P) { C0[2] = -h * b.taup * 0.5; C2[2] = -h * b.taup * 0.1; }
   else if (kind == CH_N) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); }
+  double be0[4], be1[4], be2[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     const double V2 = C2[j], V1 = C1[j] - m1 * V2, V0 = C0[j] - m0 * V1;
-    f.beta0[j] = V0 * ib0;
-    f.beta1[j] = (V1 - lo1 * f.beta0[j]) * ib1;
-    f.beta2[j] = (V2 - lo2 * f.beta1[j]) * ib2;
+    be0[j] = V0 * ib0;
+    be1[j] = (V1 - lo1 * be0[j]) * ib1;
+    be2[j] = (V2 - lo2 * be1[j]) * ib2;
+    f.beta(0, j) = be0[j]; f.beta(1, j) = be1[j]; f.beta(2, j) = be2[j];
   }
   // y-dependence of the Psi / Phi' / Pi sums.  Components (Pi, v_b) are non-zero on the Theta lane only (and Pi on
   // the ThetaP lane), so only the (Phi', Psi) components need a warp reduction.
   const int lT = ln.nq, lP = ln.nq + 1;
   double sPsi[4], sPhi[4], sPi[4], t1[4];
 #pragma unroll
-  for (int j = 0; j < 2; j++) { sPsi[j] = warp_sum(b.wPsi * f.beta2[j]); sPhi[j] = warp_sum(b.wPhi * f.beta0[j]); }
+  for (int j = 0; j < 2; j++) { sPsi[j] = warp_sum(b.wPsi * be2[j]); sPhi[j] = warp_sum(b.wPhi * be0[j]); }
   const double wPsiT = shfl_d(b.wPsi, lT), wPhiT = shfl_d(b.wPhi, lT);
 #pragma unroll
-  for (int j = 2; j < 4; j++) { sPsi[j] = wPsiT * shfl_d(f.beta2[j], lT); sPhi[j] = wPhiT * shfl_d(f.beta0[j], lT); }
+  for (int j = 2; j < 4; j++) { sPsi[j] = wPsiT * shfl_d(be2[j], lT); sPhi[j] = wPhiT * shfl_d(be0[j], lT); }
 #pragma unroll
-  for (int j = 0; j < 4; j++) { sPi[j] = shfl_d(f.beta2[j], lT); t1[j] = shfl_d(f.beta1[j], lT); }
-  sPi[2] += shfl_d(f.beta2[2] + f.beta0[2], lP);
+  for (int j = 0; j < 4; j++) { sPi[j] = shfl_d(be2[j], lT); t1[j] = shfl_d(be1[j], lT); }
+  sPi[2] += shfl_d(be2[2] + be0[2], lP);
   const double Oc = b.Oc_a, Ob = b.Ob_a;
   const double hk = f.hkap;
   const double dPhi_y[4] = {h, 0, 0, 0};
@@ -762,12 +769,13 @@ __device__ __forceinline__ void solve_reg(const Lane& ln, const BgS& b, const Re
   for (int l = MAXLEN - 1; l >= 3; l--) {
     const double up = TR::top(kind, l) ? 0.0 : f.hk * (1.0 - RLc(l));
     const double v = rr[l] - (up * ibn) * rn;
-    rr[l] = v; rn = v; ibn = f.ibv[l];
+    rr[l] = v; rn = v; ibn = f.ibv(l);
   }
   const double r2 = rr[2] - (f.hk * (1.0 - RLc(2)) * ibn) * rn;
-  const double r1 = rr[1] - (f.hk * (1.0 - RLc(1)) * f.ibv[2]) * r2;
-  const double r0 = rr[0] - (f.hk * f.ibv[1]) * r1;
-  const double a0 = r0 * f.ibv[0], a1 = (r1 - f.lo1 * a0) * f.ibv[1], a2 = (r2 - f.lo2 * a1) * f.ibv[2];
+  const double ib0 = f.ibv(0), ib1 = f.ibv(1), ib2 = f.ibv(2);
+  const double r1 = rr[1] - (f.hk * (1.0 - RLc(1)) * ib2) * r2;
+  const double r0 = rr[0] - (f.hk * ib1) * r1;
+  const double a0 = r0 * ib0, a1 = (r1 - f.lo1 * a0) * ib1, a2 = (r2 - f.lo2 * a1) * ib2;
   const int lT = ln.nq, lP = ln.nq + 1;
   const double sPsi = warp_sum(b.wPsi * a2);
   const double sPhi = warp_sum(b.wPhi * a0);
@@ -790,13 +798,13 @@ __device__ __forceinline__ void solve_reg(const Lane& ln, const BgS& b, const Re
   r5[4] = y[3];
   double U0 = a0, U1 = a1, U2 = a2;
 #pragma unroll
-  for (int j = 0; j < 4; j++) { U0 += f.beta0[j] * y[j]; U1 += f.beta1[j] * y[j]; U2 += f.beta2[j] * y[j]; }
+  for (int j = 0; j < 4; j++) { U0 += f.beta(0, j) * y[j]; U1 += f.beta(1, j) * y[j]; U2 += f.beta(2, j) * y[j]; }
   rr[0] = U0; rr[1] = U1; rr[2] = U2;
   double Up = U2;
 #pragma unroll
   for (int l = 3; l < MAXLEN; l++) {
     const double lo = TR::top(kind, l) ? -f.hk : -f.hk * RLc(l);
-    const double U = (rr[l] - lo * Up) * f.ibv[l];
+    const double U = (rr[l] - lo * Up) * f.ibv(l);
     rr[l] = U; Up = U;
   }
 }
@@ -827,9 +835,14 @@ template <class TR>
 __host__ __device__ constexpr int k1_array_len(int n) { return TR::MAXLEN > 0 ? TR::MAXLEN * TR::NCH + 8 : n; }
 template <class TR>
 __host__ __device__ constexpr int k1_num_arrays() { return TR::MAXLEN > 0 ? 7 : 9; }
+// extra doubles per warp: the lane-private factor scratch of the register path
+template <class TR>
+__host__ __device__ constexpr int k1_extra_doubles() { return TR::MAXLEN > 0 ? (TR::MAXLEN + 12) * 32 : 0; }
 
-// K1_MINBLOCKS: resident warps per SM the register allocator must allow.  8 (255 registers, no spills) measured faster than
-// 12 or 16 (168 / 128 registers with ~1-2 KB of spills) in both the latency- and the throughput-bound regime (profiles/).
+// K1_MINBLOCKS: resident warps per SM the register allocator must allow.  8 (254 registers, no spills) measured faster than
+// 12 (168 registers: 9-12 warps all land there because registers are allocated per SM sub-partition; ~450 B of spills even
+// with the factor state in shared memory and the compact NCH=18 layout) in both the latency- and the throughput-bound regime:
+// 296 / 2000 / 8000 modes 39.8 / 56.9 / 185.6 ms at 8 warps vs 55.4 / 85.1 / 209.1 ms at 12 (profiles/r1_k1_hierarchy.md).
 #ifndef K1_MINBLOCKS
 #define K1_MINBLOCKS 8
 #endif
@@ -945,9 +958,11 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
       if constexpr (MAXLEN > 0) {
         // ---------------- register-resident stages ----------------
         RegFactor<TR> f;
+        f.fs = sm + (size_t)7 * na + ln.lane;
         BgS bf;
         double rr[MAXLEN], r5[5];
-        const int lo_ = ln.lane;   // lane offset inside a row of the interleaved layout
+        const int lo_ = ln.base;   // column of the lane inside a row of the interleaved layout
+        const bool live = (NCH == 32) || ln.kind != CH_IDLE;    // compact layout: idle lanes own no column and never touch memory
         for (int s = 1; s <= 6; s++) {
           double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
           if (s <= 5) {
@@ -957,8 +972,9 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
 #pragma unroll
             for (int l = 0; l < MAXLEN; l++) {
               const int idx = lo_ + l * NCH;      // padded rows / idle lanes hold zeros
-              const double v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
-              rr[l] = v; zout[idx] = v;
+              double v = 0.0;
+              if (live) { v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx]; zout[idx] = v; }
+              rr[l] = v;
             }
 #pragma unroll
             for (int j = 0; j < 5; j++) {
@@ -976,9 +992,13 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
 #pragma unroll
             for (int l = 0; l < MAXLEN; l++) {
               const int idx = lo_ + l * NCH;
-              const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
-              rr[l] = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
-              Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
+              double e = 0.0;
+              if (live) {
+                const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
+                e = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
+                Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
+              }
+              rr[l] = e;
             }
 #pragma unroll
             for (int j = 0; j < 5; j++) {
@@ -992,7 +1012,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
           solve_reg<TR>(ln, bf, f, rr, r5);
           if (s <= 5) {
 #pragma unroll
-            for (int l = 0; l < MAXLEN; l++) { const int idx = lo_ + l * NCH; zout[idx] = (rr[l] - zout[idx]) * (1.0 / KC_GAMMA); }
+            for (int l = 0; l < MAXLEN; l++) if (live) { const int idx = lo_ + l * NCH; zout[idx] = (rr[l] - zout[idx]) * (1.0 / KC_GAMMA); }
             // every lane holds identical scalars and stores them itself (same value, same address): a lane later reads
             // back what it wrote, so no warp-level synchronisation is needed anywhere in the stage loop
 #pragma unroll
@@ -1005,8 +1025,10 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
 #pragma unroll
           for (int l = 0; l < MAXLEN; l++) {
             const int idx = lo_ + l * NCH;
-            const double sc = abstol + reltol * fmax(fabs(U[idx]), fabs(Z1[idx]));
-            const double q = rr[l] * fast_rcp(sc); ssum += q * q;
+            if (live) {
+              const double sc = abstol + reltol * fmax(fabs(U[idx]), fabs(Z1[idx]));
+              const double q = rr[l] * fast_rcp(sc); ssum += q * q;
+            }
           }
           if (ln.lane < 5) {
             double e = r5[0]; e = (ln.lane == 1) ? r5[1] : e; e = (ln.lane == 2) ? r5[2] : e; e = (ln.lane == 3) ? r5[3] : e; e = (ln.lane == 4) ? r5[4] : e;

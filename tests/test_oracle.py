@@ -57,19 +57,23 @@ def test_oracle_vs_class_massive_neutrinos(cosmo, oracle):
     _mnu_check(cosmo, out["u_hist"][0])
 
 
-def camb_pk_at(kh):
+def camb_pk_nodes(kmin_h=1e-3, kmax_h=0.5, every=1):
+    """CAMB's own k nodes [h/Mpc] and P [(Mpc/h)³]: the table has only 50 log-spaced points, so interpolating it across the
+    BAO wiggles costs up to 3 % -- the pin is taken AT the nodes."""
     g = load_golden("camb_pk.npz")
-    return np.exp(np.interp(np.log(kh), np.log(g["k_h"]), np.log(g["pk_h3"])))
+    m = (g["k_h"] >= kmin_h) & (g["k_h"] <= kmax_h)
+    return g["k_h"][m][::every], g["pk_h3"][m][::every]
 
 
 def test_oracle_plin_vs_camb(cosmo, oracle):
     """Extra pin: the reference has no automated test of plin; its data directory holds CAMB's z = 0 matter power
-    spectrum (scripts/first_plin.jl plots the ratio).  plin defaults (ℓᵧ = ℓ_ν = 50, ℓ_mν = 20, reltol 1e-5), P in (Mpc/h)³."""
+    spectrum (scripts/first_plin.jl plots the ratio).  plin defaults (ℓᵧ = ℓ_ν = 50, ℓ_mν = 20, reltol 1e-5), P in (Mpc/h)³.
+    Measured: within 0.24 % at all 27 nodes in 1e-3 ≤ k ≤ 0.5 h/Mpc."""
     from bolt_b200 import abi
-    kh = np.array([0.01, 0.05, 0.2])
+    kh, pk_camb = camb_pk_nodes(every=3)
     pk, st, _ = oracle.plin(kh * cosmo.par.h, abi.make_opts(50, 50, 20, reltol=1e-5, abstol=1e-6))
     assert np.all(st == 0)
-    assert np.abs(pk * cosmo.par.h ** 3 / camb_pk_at(kh) - 1).max() < 5e-3
+    assert np.abs(pk * cosmo.par.h ** 3 / pk_camb - 1).max() < 4e-3
 
 
 def test_oracle_cl_vs_camb(cosmo, oracle):
