@@ -231,7 +231,9 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
     if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15, K1_NCH>>(ctx, p);         // l_gamma = 8: the reference default
     if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15, K1_NCH>>(ctx, p);       // l_gamma = 10: BASELINE config 1
   }
-  return launch_k1<Trunc<0, 0, 0, 0>>(ctx, p);                            // any truncation (plin: 50, 50, 20)
+  // any other truncation (plin: 50/50/20, C4: 50/8/10): the runtime-truncation path needs l_max >= 2 on every chain
+  if (!force_generic && p.L >= 2 && p.Lnu >= 2 && p.Lm >= 2) return launch_k1<TruncRT>(ctx, p);
+  return launch_k1<Trunc<0, 0, 0, 0>>(ctx, p);
 }
 int launch_hierarchy(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, const int* d_order, int nk, const bolt_opts* o,
                      double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status, long long* d_nsteps,

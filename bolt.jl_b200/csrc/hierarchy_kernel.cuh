@@ -602,6 +602,7 @@ struct Trunc {
   // row stride of the interleaved shared-memory layout: one private column per LANE (not per chain), so idle lanes and the
   // padded rows of short chains can run the unguarded, branch-free code on zeros
   static constexpr int NCH = NCH_;     // 32 in the value kernel; NQ+3 (compact, idle lanes guarded) in the dual kernel
+  static constexpr bool RT = false;
   // row l is the truncation row / an existing row of the lane's chain
   static __device__ __forceinline__ bool top(int kind, int l) {
     return (l == LG_ && (kind == CH_T || kind == CH_P)) || (l == LNU_ && kind == CH_N) || (l == LMNU_ && kind == CH_M);
@@ -809,6 +810,184 @@ __device__ __forceinline__ void solve_reg(const Lane& ln, const BgS& b, const Re
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Runtime-truncation stage solver ("long-chain path"): any l_gamma / l_nu / l_mnu >= 2 (plin: 50/50/20, the C4 sweep: 50/8/10).
+// Same algebra and the same hoisted background / reciprocal / per-solve elimination as the register-resident solver, but the
+// chain rows stay in the warp's shared memory in the reference's own order (n doubles per array, nothing padded) and the
+// sweeps are runtime loops over l.  Factorisation and the downward elimination of the right-hand side share one pass (both
+// need up_l * ib_{l+1}).
+// ---------------------------------------------------------------------------------------------------
+struct TruncRT {
+  static constexpr int LG = 0, LNU = 0, LMNU = 0, NQ = 0, MAXL = 0, MAXLEN = 0, NCH = 32;
+  static constexpr bool RT = true;
+};
+
+struct RtFactor {
+  double* bs;                 // lane-private column of the beta scratch: beta_row[j] at bs[(4*row + j) * 32]
+  double M[4][4];
+  double h, hk, hkap, vden, e4c, lo1, lo2, dtau, btr;
+  __device__ __forceinline__ double& beta(int row, int j) const { return bs[(4 * row + j) * 32]; }
+};
+
+// Rows len-1 .. 3 of the lane's chain: (FACT) inverse pivots into ib[], and the downward elimination of r[].
+// Returns the state the bottom rows continue from.
+template <bool FACT>
+__device__ __forceinline__ void rt_down(const Lane& ln, const RtFactor& f, double* ib, double* r, double& ibn, double& lo_next, double& rn) {
+  ibn = 0.0; lo_next = 0.0; rn = 0.0;
+  const int len = ln.len;
+#pragma unroll 4
+  for (int l = ln.maxlen - 1; l >= 3; l--) {
+    if (l < len) {
+      const int idx = ln.base + l * ln.stride;
+      const bool top = (l == len - 1);
+      const double rl = c_rl[l];
+      const double up = top ? 0.0 : f.hk * (1.0 - rl);
+      const double m = up * ibn;
+      double ibl;
+      if (FACT) {
+        const double bd = top ? f.btr : 1.0 + f.dtau;
+        ibl = fast_rcp(bd - m * lo_next);
+        ib[idx] = ibl;
+        lo_next = top ? -f.hk : -f.hk * rl;
+      } else ibl = ib[idx];
+      const double v = r[idx] - m * rn;
+      r[idx] = v; rn = v; ibn = ibl;
+    }
+  }
+}
+
+// Factor W = I - h A(x_s) and eliminate r[] downward in the same pass.
+__device__ __forceinline__ void rt_factor_down(const Lane& ln, const BgS& b, double h, RtFactor& f, double* ib, double* r,
+                                               double& r0, double& r1, double& r2) {
+  const int kind = ln.kind;
+  const bool photon = (kind == CH_T || kind == CH_P);
+  const bool live = kind != CH_IDLE;
+  f.h = h; f.hk = h * b.kappa * b.qe; f.hkap = h * b.kappa; f.vden = fast_rcp(1.0 + h);
+  f.e4c = -3.0 * h * b.taup * b.R;
+  f.dtau = photon ? -h * b.taup : 0.0;
+  f.btr = 1.0 + h * (double)ln.len * b.iHeta + f.dtau;
+  double ibn, lo_next, rn;
+  rt_down<true>(ln, f, ib, r, ibn, lo_next, rn);
+  const bool top2 = (ln.len == 3);      // l = 2 is the truncation row of a chain with l_max = 2
+  const double dtau = f.dtau;
+  const double up2 = top2 ? 0.0 : f.hk * (1.0 - RLc(2)), up1 = f.hk * (1.0 - RLc(1)), up0 = f.hk;
+  const double lo2 = top2 ? -f.hk : -f.hk * RLc(2), lo1 = -f.hk * RLc(1);
+  const double mm2 = up2 * ibn;
+  const double ib2 = live ? fast_rcp((top2 ? f.btr : 1.0 + dtau) - mm2 * lo_next) : 0.0;
+  const double m1 = up1 * ib2;
+  const double ib1 = live ? fast_rcp((1.0 + dtau) - m1 * lo2) : 0.0;
+  const double m0 = up0 * ib1;
+  const double ib0 = live ? fast_rcp((1.0 + (kind == CH_P ? dtau : 0.0)) - m0 * lo1) : 0.0;
+  f.lo1 = lo1; f.lo2 = lo2;
+  r2 = 0.0; r1 = 0.0; r0 = 0.0;
+  if (live) {
+    const int i0 = ln.base, i1 = i0 + ln.stride, i2 = i1 + ln.stride;
+    ib[i2] = ib2; ib[i1] = ib1; ib[i0] = ib0;
+    r2 = r[i2] - mm2 * rn; r1 = r[i1] - m1 * r2; r0 = r[i0] - m0 * r1;
+  }
+  double C0[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0};
+  if (kind == CH_M) { C0[0] = h * ln.df0; C1[1] = -f.hkap * (1.0 / 3.0) * b.eq * ln.df0; }
+  else if (kind == CH_T) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); C1[3] = h * b.taup * (1.0 / 3.0); C2[2] = -h * b.taup * 0.1; }
+  else if (kind == CH_P) { C0[2] = -h * b.taup * 0.5; C2[2] = -h * b.taup * 0.1; }
+  else if (kind == CH_N) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); }
+  double be0[4], be1[4], be2[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const double V2 = C2[j], V1 = C1[j] - m1 * V2, V0 = C0[j] - m0 * V1;
+    be0[j] = V0 * ib0;
+    be1[j] = (V1 - lo1 * be0[j]) * ib1;
+    be2[j] = (V2 - lo2 * be1[j]) * ib2;
+    f.beta(0, j) = be0[j]; f.beta(1, j) = be1[j]; f.beta(2, j) = be2[j];
+  }
+  const int lT = ln.nq, lP = ln.nq + 1;
+  double sPsi[4], sPhi[4], sPi[4], t1[4];
+#pragma unroll
+  for (int j = 0; j < 2; j++) { sPsi[j] = warp_sum(b.wPsi * be2[j]); sPhi[j] = warp_sum(b.wPhi * be0[j]); }
+  const double wPsiT = shfl_d(b.wPsi, lT), wPhiT = shfl_d(b.wPhi, lT);
+#pragma unroll
+  for (int j = 2; j < 4; j++) { sPsi[j] = wPsiT * shfl_d(be2[j], lT); sPhi[j] = wPhiT * shfl_d(be0[j], lT); }
+#pragma unroll
+  for (int j = 0; j < 4; j++) { sPi[j] = shfl_d(be2[j], lT); t1[j] = shfl_d(be1[j], lT); }
+  sPi[2] += shfl_d(be2[2] + be0[2], lP);
+  const double Oc = b.Oc_a, Ob = b.Ob_a;
+  const double hk = f.hkap;
+  const double dPhi_y[4] = {h, 0, 0, 0};
+  const double dDel_y[4] = {-3.0 * h, -hk * hk * f.vden, 0, 0};
+  const double dDb_y[4] = {-3.0 * h, 0, 0, hk};
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    f.M[0][j] = dPhi_y[j] + b.cPsi * sPsi[j] + (j == 1 ? 1.0 : 0.0);
+    f.M[1][j] = (j == 0 ? 1.0 : 0.0) - (j == 1 ? 1.0 : 0.0) + b.k2 * dPhi_y[j] - b.gPhi * (Oc * dDel_y[j] + Ob * dDb_y[j] + sPhi[j]);
+    f.M[2][j] = (j == 2 ? 1.0 : 0.0) - sPi[j];
+    f.M[3][j] = (j == 3 ? (1.0 + h - h * b.taup * b.R) : 0.0) + hk * ((j == 1 ? 1.0 : 0.0) + b.csb2 * dDb_y[j]) + f.e4c * t1[j];
+  }
+}
+
+// Downward elimination only (the smoothing solve of the error estimate re-uses the last stage's factorisation).
+__device__ __forceinline__ void rt_down_only(const Lane& ln, const RtFactor& f, double* ib, double* r, double& r0, double& r1, double& r2) {
+  double ibn, lo_next, rn;
+  rt_down<false>(ln, f, ib, r, ibn, lo_next, rn);
+  r2 = 0.0; r1 = 0.0; r0 = 0.0;
+  if (ln.kind != CH_IDLE) {
+    const int i0 = ln.base, i1 = i0 + ln.stride, i2 = i1 + ln.stride;
+    const bool top2 = (ln.len == 3);
+    const double up2 = top2 ? 0.0 : f.hk * (1.0 - RLc(2));
+    r2 = r[i2] - (up2 * ibn) * rn;
+    r1 = r[i1] - (f.hk * (1.0 - RLc(1)) * ib[i2]) * r2;
+    r0 = r[i0] - (f.hk * ib[i1]) * r1;
+  }
+}
+
+// Border solve and upward sweep.  ZMODE: zout[idx] holds the stage's right-hand side and receives z = (U - rhs)/gamma;
+// otherwise U is written to r[] (error smoothing).  r5[] are the five metric/matter scalars (same copy on every lane).
+template <bool ZMODE>
+__device__ __forceinline__ void rt_finish(const Lane& ln, const BgS& b, const RtFactor& f, const double* ib, double* r, double* zout,
+                                          double r0, double r1, double r2, double (&r5)[5]) {
+  const bool live = ln.kind != CH_IDLE;
+  double ib0 = 0.0, ib1 = 0.0, ib2 = 0.0;
+  const int i0 = ln.base, i1 = i0 + ln.stride, i2 = i1 + ln.stride;
+  if (live) { ib0 = ib[i0]; ib1 = ib[i1]; ib2 = ib[i2]; }
+  const double a0 = r0 * ib0, a1 = (r1 - f.lo1 * a0) * ib1, a2 = (r2 - f.lo2 * a1) * ib2;
+  const int lT = ln.nq, lP = ln.nq + 1;
+  const double sPsi = warp_sum(b.wPsi * a2);
+  const double sPhi = warp_sum(b.wPhi * a0);
+  const double sPi = shfl_d(a2, lT) + shfl_d(a2 + a0, lP);
+  const double t1 = shfl_d(a1, lT);
+  const double rPhi = r5[0], rdel = r5[1], rv = r5[2], rdb = r5[3], rvb = r5[4];
+  const double hk = f.hkap, h = f.h;
+  const double vc = rv * f.vden, dc = rdel + hk * vc;
+  double rhs[4], y[4];
+  rhs[0] = -(rPhi + b.cPsi * sPsi);
+  rhs[1] = -(b.k2 * rPhi - b.gPhi * (b.Oc_a * dc + b.Ob_a * rdb + sPhi));
+  rhs[2] = sPi;
+  rhs[3] = -(hk * b.csb2 * rdb + f.e4c * t1 - rvb);
+  ge4(f.M, rhs, y);
+  r5[0] = rPhi + h * y[0];
+  const double v = vc - hk * f.vden * y[1];
+  r5[1] = rdel + hk * v - 3.0 * h * y[0];
+  r5[2] = v;
+  r5[3] = rdb - 3.0 * h * y[0] + hk * y[3];
+  r5[4] = y[3];
+  if (live) {
+    double U0 = a0, U1 = a1, U2 = a2;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { U0 += f.beta(0, j) * y[j]; U1 += f.beta(1, j) * y[j]; U2 += f.beta(2, j) * y[j]; }
+    if (ZMODE) {
+      zout[i0] = (U0 - zout[i0]) * (1.0 / KC_GAMMA); zout[i1] = (U1 - zout[i1]) * (1.0 / KC_GAMMA); zout[i2] = (U2 - zout[i2]) * (1.0 / KC_GAMMA);
+    } else { r[i0] = U0; r[i1] = U1; r[i2] = U2; }
+    double Up = U2;
+    const int len = ln.len;
+#pragma unroll 4
+    for (int l = 3; l < len; l++) {
+      const int idx = ln.base + l * ln.stride;
+      const double lo = (l == len - 1) ? -f.hk : -f.hk * c_rl[l];
+      const double U = (r[idx] - lo * Up) * ib[idx];
+      if (ZMODE) zout[idx] = (U - zout[idx]) * (1.0 / KC_GAMMA); else r[idx] = U;
+      Up = U;
+    }
+  }
+}
+
 // Chain ownership of a lane for cosmology c.  MAXLEN == 0: generic layout = the reference's unpack order.
 // MAXLEN > 0: interleaved layout [l][chain] (+5 scalars after MAXLEN*NCH) for the register-resident solver.
 template <class TR>
@@ -837,7 +1016,7 @@ template <class TR>
 __host__ __device__ constexpr int k1_num_arrays() { return TR::MAXLEN > 0 ? 7 : 9; }
 // extra doubles per warp: the lane-private factor scratch of the register path
 template <class TR>
-__host__ __device__ constexpr int k1_extra_doubles() { return TR::MAXLEN > 0 ? (TR::MAXLEN + 12) * 32 : 0; }
+__host__ __device__ constexpr int k1_extra_doubles() { return TR::MAXLEN > 0 ? (TR::MAXLEN + 12) * 32 : (TR::RT ? 12 * 32 : 0); }
 
 // K1_MINBLOCKS: resident warps per SM the register allocator must allow.  8 (254 registers, no spills) measured faster than
 // 12 (168 registers: 9-12 warps all land there because registers are allocated per SM sub-partition; ~450 B of spills even
@@ -1038,6 +1217,56 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
           }
           EEst = sqrt(warp_sum(ssum) / n);
         }
+      } else if constexpr (TR::RT) {
+        // ---------------- runtime-truncation stages (long chains; rows in shared memory) ----------------
+        RtFactor f;
+        f.bs = sm + (size_t)9 * na + ln.lane;
+        BgS bf;
+        double r5[5], q5[5], r0, r1, r2;
+        const int len = ln.len, iS = ln.iS;
+        for (int s = 1; s <= 6; s++) {
+          double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
+          if (s <= 5) {
+            const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
+            auto rhs_of = [&](int idx) {           // terms of later stages skipped (uniform predicates)
+              double v = U[idx] + a0 * Z0[idx];
+              if (s > 1) v += a1 * Z1[idx];
+              if (s > 2) v += a2 * Z2[idx];
+              if (s > 3) v += a3 * Z3[idx];
+              if (s > 4) v += a4 * Z4[idx];
+              return v;
+            };
+#pragma unroll 4
+            for (int l = 0; l < len; l++) { const int idx = ln.base + l * ln.stride; const double v = rhs_of(idx); r[idx] = v; zout[idx] = v; }
+#pragma unroll
+            for (int j = 0; j < 5; j++) { const double v = rhs_of(iS + j); r5[j] = v; q5[j] = v; }
+            eval_bg_fast(c, ln, mc, x + KC_C[s] * dt, bf);
+            rsa_flag |= (ln.k * bf.eta > 240.0) && (-bf.taup * bf.H > 100.0 * bf.eta);
+            rt_factor_down(ln, bf, KC_GAMMA * dt, f, ib, r, r0, r1, r2);
+            rt_finish<true>(ln, bf, f, ib, r, zout, r0, r1, r2, r5);
+            // every lane holds the same scalars and stores them itself (same value, same address; no read-modify-write)
+#pragma unroll
+            for (int j = 0; j < 5; j++) zout[iS + j] = (r5[j] - q5[j]) * (1.0 / KC_GAMMA);
+          } else {
+            const double e0 = KC_E[0] * s1, b0 = KC_A[5][0] * s1;
+            auto pass = [&](int idx) {
+              const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
+              Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
+              return e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
+            };
+#pragma unroll 4
+            for (int l = 0; l < len; l++) { const int idx = ln.base + l * ln.stride; r[idx] = pass(idx); }
+#pragma unroll
+            for (int j = 0; j < 5; j++) r5[j] = pass(iS + j);
+            if (fixed) break;
+            rt_down_only(ln, f, ib, r, r0, r1, r2);
+            rt_finish<false>(ln, bf, f, ib, r, nullptr, r0, r1, r2, r5);
+#pragma unroll
+            for (int j = 0; j < 5; j++) r[iS + j] = r5[j];
+          }
+        }
+        __syncwarp();
+        if (!fixed) EEst = sqrt(sumsq_scaled(r, U, Z1) / n);
       } else {
         // ---------------- generic stages (runtime chain lengths, work vectors in shared memory) ----------------
         Factor f;
@@ -1099,7 +1328,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
           if (ix >= p.ix_first) {
             double th = (xs - x) / dt; if (th > 1.0) th = 1.0;
             Hermite hm = hermite_weights(th);
-            sample_sources(c, ln, p, ik, ix, xs, hm, U, Z1, Z0, s1, Z5, rsa_flag, MAXLEN > 0 ? &mc : nullptr);
+            sample_sources(c, ln, p, ik, ix, xs, hm, U, Z1, Z0, s1, Z5, rsa_flag, (MAXLEN > 0 || TR::RT) ? &mc : nullptr);
           }
           ix++;
         }
