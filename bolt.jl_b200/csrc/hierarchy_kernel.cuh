@@ -835,21 +835,21 @@ template <bool FACT>
 __device__ __forceinline__ void rt_down(const Lane& ln, const RtFactor& f, double* ib, double* r, double& ibn, double& lo_next, double& rn) {
   ibn = 0.0; lo_next = 0.0; rn = 0.0;
   const int len = ln.len;
+  if (len > 3) {                 // truncation row (l = len-1 >= 3) peeled: no coupling upward, r unchanged
+    const int idx = ln.base + (len - 1) * ln.stride;
+    if (FACT) { ibn = fast_rcp(f.btr); ib[idx] = ibn; } else ibn = ib[idx];
+    lo_next = -f.hk; rn = r[idx];
+  }
+  const double bd = 1.0 + f.dtau;
+  int idx = ln.base + (ln.maxlen - 2) * ln.stride;
 #pragma unroll 4
-  for (int l = ln.maxlen - 1; l >= 3; l--) {
-    if (l < len) {
-      const int idx = ln.base + l * ln.stride;
-      const bool top = (l == len - 1);
+  for (int l = ln.maxlen - 2; l >= 3; l--, idx -= ln.stride) {      // uniform l: c_rl[l] is a constant-bank operand
+    if (l < len - 1) {
       const double rl = c_rl[l];
-      const double up = top ? 0.0 : f.hk * (1.0 - rl);
-      const double m = up * ibn;
+      const double m = (f.hk * (1.0 - rl)) * ibn;
       double ibl;
-      if (FACT) {
-        const double bd = top ? f.btr : 1.0 + f.dtau;
-        ibl = fast_rcp(bd - m * lo_next);
-        ib[idx] = ibl;
-        lo_next = top ? -f.hk : -f.hk * rl;
-      } else ibl = ib[idx];
+      if (FACT) { ibl = fast_rcp(bd - m * lo_next); ib[idx] = ibl; lo_next = -f.hk * rl; }
+      else ibl = ib[idx];
       const double v = r[idx] - m * rn;
       r[idx] = v; rn = v; ibn = ibl;
     }
@@ -977,13 +977,16 @@ __device__ __forceinline__ void rt_finish(const Lane& ln, const BgS& b, const Rt
     } else { r[i0] = U0; r[i1] = U1; r[i2] = U2; }
     double Up = U2;
     const int len = ln.len;
+    int idx = ln.base + 3 * ln.stride;
 #pragma unroll 4
-    for (int l = 3; l < len; l++) {
-      const int idx = ln.base + l * ln.stride;
-      const double lo = (l == len - 1) ? -f.hk : -f.hk * c_rl[l];
-      const double U = (r[idx] - lo * Up) * ib[idx];
+    for (int l = 3; l < len - 1; l++, idx += ln.stride) {
+      const double U = (r[idx] + (f.hk * c_rl[l]) * Up) * ib[idx];
       if (ZMODE) zout[idx] = (U - zout[idx]) * (1.0 / KC_GAMMA); else r[idx] = U;
       Up = U;
+    }
+    if (len > 3) {               // truncation row
+      const double U = (r[idx] + f.hk * Up) * ib[idx];
+      if (ZMODE) zout[idx] = (U - zout[idx]) * (1.0 / KC_GAMMA); else r[idx] = U;
     }
   }
 }
@@ -1219,54 +1222,65 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
         }
       } else if constexpr (TR::RT) {
         // ---------------- runtime-truncation stages (long chains; rows in shared memory) ----------------
+        // Elementwise passes (stage assembly, error/u_{n+1} pass, error norm) run flat over the n entries, lane-strided and
+        // conflict-free; only the sweeps follow the chains.  __syncwarp() separates the two access patterns.
         RtFactor f;
         f.bs = sm + (size_t)9 * na + ln.lane;
         BgS bf;
         double r5[5], q5[5], r0, r1, r2;
-        const int len = ln.len, iS = ln.iS;
+        const int iS = ln.iS;
         for (int s = 1; s <= 6; s++) {
           double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
           if (s <= 5) {
             const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
-            auto rhs_of = [&](int idx) {           // terms of later stages skipped (uniform predicates)
-              double v = U[idx] + a0 * Z0[idx];
-              if (s > 1) v += a1 * Z1[idx];
-              if (s > 2) v += a2 * Z2[idx];
-              if (s > 3) v += a3 * Z3[idx];
-              if (s > 4) v += a4 * Z4[idx];
-              return v;
-            };
 #pragma unroll 4
-            for (int l = 0; l < len; l++) { const int idx = ln.base + l * ln.stride; const double v = rhs_of(idx); r[idx] = v; zout[idx] = v; }
-#pragma unroll
-            for (int j = 0; j < 5; j++) { const double v = rhs_of(iS + j); r5[j] = v; q5[j] = v; }
+            for (int i = ln.lane; i < n; i += 32) {
+              double v = U[i] + a0 * Z0[i];         // terms of later stages skipped (uniform predicates)
+              if (s > 1) v += a1 * Z1[i];
+              if (s > 2) v += a2 * Z2[i];
+              if (s > 3) v += a3 * Z3[i];
+              if (s > 4) v += a4 * Z4[i];
+              r[i] = v; zout[i] = v;
+            }
             eval_bg_fast(c, ln, mc, x + KC_C[s] * dt, bf);
             rsa_flag |= (ln.k * bf.eta > 240.0) && (-bf.taup * bf.H > 100.0 * bf.eta);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 5; j++) { r5[j] = r[iS + j]; q5[j] = r5[j]; }
             rt_factor_down(ln, bf, KC_GAMMA * dt, f, ib, r, r0, r1, r2);
             rt_finish<true>(ln, bf, f, ib, r, zout, r0, r1, r2, r5);
             // every lane holds the same scalars and stores them itself (same value, same address; no read-modify-write)
 #pragma unroll
             for (int j = 0; j < 5; j++) zout[iS + j] = (r5[j] - q5[j]) * (1.0 / KC_GAMMA);
+            __syncwarp();
           } else {
             const double e0 = KC_E[0] * s1, b0 = KC_A[5][0] * s1;
-            auto pass = [&](int idx) {
-              const double z0 = Z0[idx], z2 = Z2[idx], z3 = Z3[idx], z4 = Z4[idx], z5 = Z5[idx];
-              Z1[idx] = U[idx] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
-              return e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
-            };
 #pragma unroll 4
-            for (int l = 0; l < len; l++) { const int idx = ln.base + l * ln.stride; r[idx] = pass(idx); }
-#pragma unroll
-            for (int j = 0; j < 5; j++) r5[j] = pass(iS + j);
+            for (int i = ln.lane; i < n; i += 32) {
+              const double z0 = Z0[i], z2 = Z2[i], z3 = Z3[i], z4 = Z4[i], z5 = Z5[i];
+              Z1[i] = U[i] + b0 * z0 + KC_A[5][2] * z2 + KC_A[5][3] * z3 + KC_A[5][4] * z4 + KC_GAMMA * z5;
+              r[i] = e0 * z0 + KC_E[2] * z2 + KC_E[3] * z3 + KC_E[4] * z4 + KC_E[5] * z5;
+            }
+            __syncwarp();
             if (fixed) break;
+#pragma unroll
+            for (int j = 0; j < 5; j++) r5[j] = r[iS + j];
             rt_down_only(ln, f, ib, r, r0, r1, r2);
             rt_finish<false>(ln, bf, f, ib, r, nullptr, r0, r1, r2, r5);
 #pragma unroll
             for (int j = 0; j < 5; j++) r[iS + j] = r5[j];
+            __syncwarp();
           }
         }
-        __syncwarp();
-        if (!fixed) EEst = sqrt(sumsq_scaled(r, U, Z1) / n);
+        if (!fixed) {
+          double ssum = 0.0;
+#pragma unroll 4
+          for (int i = ln.lane; i < n; i += 32) {
+            const double sc = abstol + reltol * fmax(fabs(U[i]), fabs(Z1[i]));
+            const double q = r[i] * fast_rcp(sc); ssum += q * q;
+          }
+          EEst = sqrt(warp_sum(ssum) / n);
+        }
       } else {
         // ---------------- generic stages (runtime chain lengths, work vectors in shared memory) ----------------
         Factor f;
