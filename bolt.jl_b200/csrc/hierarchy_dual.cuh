@@ -78,11 +78,44 @@ template <int NP> struct BgD {
   double x, a;
   T H, eta, taup, taupp, csb2, Hp, kappa, qe, eq, wPsi, wPhi, cPsi, gPhi, k2, R;
 };
+// everything derived from the table values b.H, b.eta, b.taup, b.csb2 (already set) at abscissa x
+template <int NP> __device__ __forceinline__ void finish_bg_d(const DevCosmo& c, const Lane& ln, double x, BgD<NP>& b);
 template <int NP> __device__ __forceinline__ void eval_bg_d(const DevCosmo& c, const Lane& ln, double x, BgD<NP>& b) {
-  typedef Dual<NP> T;
-  b.x = x; b.a = exp(x);
   b.H = ctab_d<NP>(c, BOLT_T_H, x); b.eta = ctab_d<NP>(c, BOLT_T_eta, x); b.taup = ctab_d<NP>(c, BOLT_T_taup, x);
   b.taupp = ctab_d<NP>(c, BOLT_T_taupp, x); b.csb2 = ctab_d<NP>(c, BOLT_T_csb2, x); b.Hp = ctab_d<NP>(c, BOLT_T_Hp, x);
+  finish_bg_d<NP>(c, ln, x, b);
+}
+// Stage variant: the (1+NP) components of the four tables a stage needs (H, eta, tau', c_s^2) are evaluated by ONE lane
+// each -- lane t*(1+NP)+comp -- instead of by every lane; bg_stage_prefetch issues the loads (call it early: the value is
+// not needed before the stage value is solved), eval_bg_d_stage broadcasts.  tau'' and H' are not used by a stage.
+template <int NP> __device__ __forceinline__ double bg_stage_prefetch(const DevCosmo& c, const Lane& ln, double x) {
+  constexpr int ND = 1 + NP;
+  static_assert(4 * ND <= 32, "one (table, component) pair per lane");
+  const int which[4] = {BOLT_T_H, BOLT_T_eta, BOLT_T_taup, BOLT_T_csb2};
+  double tv = 0.0;
+  if (ln.lane < 4 * ND) {
+    const int t = ln.lane / ND, comp = ln.lane - t * ND;
+    const int tab = (t == 0) ? which[0] : (t == 1) ? which[1] : (t == 2) ? which[2] : which[3];
+    const double* cp = comp == 0 ? c.tab[tab] : c.dtab[tab] + (size_t)(comp - 1) * (c.n_x + 2);
+    tv = spline_eval(cp, c.n_x, c.x0, c.dx, x);
+  }
+  return tv;
+}
+template <int NP> __device__ __forceinline__ void eval_bg_d_stage(const DevCosmo& c, const Lane& ln, double x, double tv, BgD<NP>& b) {
+  constexpr int ND = 1 + NP;
+  auto fetch = [&](int t) {
+    Dual<NP> r; r.v = shfl_d(tv, t * ND);
+#pragma unroll
+    for (int j = 0; j < NP; j++) r.d[j] = shfl_d(tv, t * ND + 1 + j);
+    return r;
+  };
+  b.H = fetch(0); b.eta = fetch(1); b.taup = fetch(2); b.csb2 = fetch(3);
+  b.taupp = Dual<NP>(0.0); b.Hp = Dual<NP>(0.0);
+  finish_bg_d<NP>(c, ln, x, b);
+}
+template <int NP> __device__ __forceinline__ void finish_bg_d(const DevCosmo& c, const Lane& ln, double x, BgD<NP>& b) {
+  typedef Dual<NP> T;
+  b.x = x; b.a = exp(x);
   b.kappa = ln.k / b.H;
   const T Om_r = cs_d<NP>(c, BOLT_S_Omega_r), Om_b = cs_d<NP>(c, BOLT_S_Omega_b), rho_crit = cs_d<NP>(c, BOLT_S_rho_crit);
   const T H0 = cs_d<NP>(c, BOLT_S_H0);

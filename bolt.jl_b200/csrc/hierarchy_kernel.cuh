@@ -1062,7 +1062,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
 #define SLOT_Z0 (sm + (flipZ ? (size_t)6 * na : (size_t)na))
 #define SLOT_Z5 (sm + (flipZ ? (size_t)na : (size_t)6 * na))
     double* U = SLOT_U; double* Z0 = SLOT_Z0; double* Z1 = SLOT_Z1; double* Z5 = SLOT_Z5;
-    if constexpr (MAXLEN > 0) {   // zero-coefficient terms are still loaded by the branch-free stage assembly
+    if constexpr (MAXLEN > 0 || TR::RT) {   // zero-coefficient terms are still loaded by the branch-free stage assembly
       for (int i = ln.lane; i < 7 * na; i += 32) sm[i] = 0.0;
       __syncwarp();
     }
@@ -1235,11 +1235,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
             const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
 #pragma unroll 4
             for (int i = ln.lane; i < n; i += 32) {
-              double v = U[i] + a0 * Z0[i];         // terms of later stages skipped (uniform predicates)
-              if (s > 1) v += a1 * Z1[i];
-              if (s > 2) v += a2 * Z2[i];
-              if (s > 3) v += a3 * Z3[i];
-              if (s > 4) v += a4 * Z4[i];
+              const double v = U[i] + a0 * Z0[i] + a1 * Z1[i] + a2 * Z2[i] + a3 * Z3[i] + a4 * Z4[i];   // zero coefficients: branch-free
               r[i] = v; zout[i] = v;
             }
             eval_bg_fast(c, ln, mc, x + KC_C[s] * dt, bf);
