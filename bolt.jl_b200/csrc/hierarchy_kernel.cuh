@@ -841,18 +841,20 @@ __device__ __forceinline__ void rt_down(const Lane& ln, const RtFactor& f, doubl
     lo_next = -f.hk; rn = r[idx];
   }
   const double bd = 1.0 + f.dtau;
-  int idx = ln.base + (ln.maxlen - 2) * ln.stride;
+  // Uniform loop over l (c_rl[l] is a constant-bank operand), branch-free: a lane whose chain does not reach row l works on
+  // its own element 0 (always a valid address), keeps its carried state by selects and has its stores predicated off.
 #pragma unroll 4
-  for (int l = ln.maxlen - 2; l >= 3; l--, idx -= ln.stride) {      // uniform l: c_rl[l] is a constant-bank operand
-    if (l < len - 1) {
-      const double rl = c_rl[l];
-      const double m = (f.hk * (1.0 - rl)) * ibn;
-      double ibl;
-      if (FACT) { ibl = fast_rcp(bd - m * lo_next); ib[idx] = ibl; lo_next = -f.hk * rl; }
-      else ibl = ib[idx];
-      const double v = r[idx] - m * rn;
-      r[idx] = v; rn = v; ibn = ibl;
-    }
+  for (int l = ln.maxlen - 2; l >= 3; l--) {
+    const bool act = l < len - 1;
+    const int idx = ln.base + (act ? l : 0) * ln.stride;
+    const double rl = c_rl[l];
+    const double m = (f.hk * (1.0 - rl)) * ibn;
+    double ibl;
+    if (FACT) { ibl = fast_rcp(bd - m * lo_next); if (act) ib[idx] = ibl; lo_next = act ? -f.hk * rl : lo_next; }
+    else ibl = ib[idx];
+    const double v = r[idx] - m * rn;
+    if (act) r[idx] = v;
+    rn = act ? v : rn; ibn = act ? ibl : ibn;
   }
 }
 
@@ -968,6 +970,7 @@ __device__ __forceinline__ void rt_finish(const Lane& ln, const BgS& b, const Rt
   r5[2] = v;
   r5[3] = rdb - 3.0 * h * y[0] + hk * y[3];
   r5[4] = y[3];
+  double U2s = 0.0;
   if (live) {
     double U0 = a0, U1 = a1, U2 = a2;
 #pragma unroll
@@ -975,16 +978,22 @@ __device__ __forceinline__ void rt_finish(const Lane& ln, const BgS& b, const Rt
     if (ZMODE) {
       zout[i0] = (U0 - zout[i0]) * (1.0 / KC_GAMMA); zout[i1] = (U1 - zout[i1]) * (1.0 / KC_GAMMA); zout[i2] = (U2 - zout[i2]) * (1.0 / KC_GAMMA);
     } else { r[i0] = U0; r[i1] = U1; r[i2] = U2; }
-    double Up = U2;
+    U2s = U2;
+  }
+  // upward sweep: uniform and branch-free like the downward one (idle lanes: base = stride = len = 0, nothing stored)
+  {
+    double Up = live ? U2s : 0.0;
     const int len = ln.len;
-    int idx = ln.base + 3 * ln.stride;
 #pragma unroll 4
-    for (int l = 3; l < len - 1; l++, idx += ln.stride) {
+    for (int l = 3; l < ln.maxlen - 1; l++) {
+      const bool act = l < len - 1;
+      const int idx = ln.base + (act ? l : 0) * ln.stride;
       const double U = (r[idx] + (f.hk * c_rl[l]) * Up) * ib[idx];
-      if (ZMODE) zout[idx] = (U - zout[idx]) * (1.0 / KC_GAMMA); else r[idx] = U;
-      Up = U;
+      if (act) { if (ZMODE) zout[idx] = (U - zout[idx]) * (1.0 / KC_GAMMA); else r[idx] = U; }
+      Up = act ? U : Up;
     }
     if (len > 3) {               // truncation row
+      const int idx = ln.base + (len - 1) * ln.stride;
       const double U = (r[idx] + f.hk * Up) * ib[idx];
       if (ZMODE) zout[idx] = (U - zout[idx]) * (1.0 / KC_GAMMA); else r[idx] = U;
     }
