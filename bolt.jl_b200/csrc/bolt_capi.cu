@@ -209,7 +209,7 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   for (int j = 0; j < MAX_NP; j++) p.comp_map[j] = (comp_map && j < np) ? comp_map[j] : 1 + j;
   if (np > 0) {     // value + gradient in one pass
     if (!getenv("BOLT_K1_GENERIC") && nq == 15 && p.L == 8 && p.Lnu == 8 && p.Lm == 10) {     // register-resident (hierarchy_dual_reg.cuh)
-      typedef Trunc<8, 8, 10, 15, 18> TRD;
+      typedef Trunc<8, 8, 10, 15, 19> TRD;
       switch (np) {
         case 1: return launch_k1_dual_reg<TRD, 1>(ctx, p);
         case 2: return launch_k1_dual_reg<TRD, 2>(ctx, p);

@@ -601,7 +601,7 @@ struct Trunc {
   static constexpr int MAXLEN = (NQ_ > 0) ? MAXL + 1 : 0;     // 0 = generic (runtime) kernel
   // row stride of the interleaved shared-memory layout: one private column per LANE (not per chain), so idle lanes and the
   // padded rows of short chains can run the unguarded, branch-free code on zeros
-  static constexpr int NCH = NCH_;     // 32 in the value kernel; NQ+3 (compact, idle lanes guarded) in the dual kernel
+  static constexpr int NCH = NCH_;     // 32 in the value kernel; NQ+4 (compact + one shared all-zero column for the idle lanes) in the dual kernel
   static constexpr bool RT = false;
   // row l is the truncation row / an existing row of the lane's chain
   static __device__ __forceinline__ bool top(int kind, int l) {
@@ -1015,8 +1015,10 @@ __device__ __forceinline__ void lane_setup(const DevCosmo& c, const SolveParams&
   else if (ln.lane == c.nq + 2) { ln.kind = CH_N; ln.rbase = 2 * (p.L + 1); ln.rstride = 1; ln.len = p.Lnu + 1; }
   else { ln.kind = CH_IDLE; ln.rbase = 0; ln.rstride = 0; ln.len = 0; }
   if constexpr (TR::MAXLEN > 0) {
-    const bool own = (TR::NCH == 32) || ln.kind != CH_IDLE;     // compact layout: idle lanes own no column
+    const bool own = (TR::NCH == 32) || ln.kind != CH_IDLE;     // compact layout: idle lanes own no column ...
     ln.base = own ? ln.lane : 0; ln.stride = own ? TR::NCH : 0; ln.iS = TR::MAXLEN * TR::NCH;
+    // ... or (NCH = NQ + 4) share one dummy column that only ever holds zeros, so that the kernel needs no idle-lane guards
+    if (TR::NCH == TR::NQ + 4 && !own) { ln.base = TR::NCH - 1; ln.stride = TR::NCH; }
   }
   else { ln.base = ln.rbase; ln.stride = ln.rstride; ln.iS = ln.riS; }
 }
