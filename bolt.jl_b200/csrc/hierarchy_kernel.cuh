@@ -630,8 +630,10 @@ struct BgS {
 };
 __device__ __forceinline__ void eval_bg_fast(const DevCosmo& c, const Lane& ln, const ModeConst& mc, double x, BgS& b) {
   const int which[4] = {BOLT_T_H, BOLT_T_eta, BOLT_T_taup, BOLT_T_csb2};
-  double v = 0.0;
-  if (ln.lane < 4) v = spline_eval(c.tab[which[ln.lane]], c.n_x, c.x0, c.dx, x);
+  // every lane evaluates one of the four tables (lane & 3): no divergent branch, the extra loads are broadcasts
+  const int wl = ln.lane & 3;
+  const int tab = (wl == 0) ? which[0] : (wl == 1) ? which[1] : (wl == 2) ? which[2] : which[3];
+  const double v = spline_eval(c.tab[tab], c.n_x, c.x0, c.dx, x);
   b.H = shfl_d(v, 0); b.eta = shfl_d(v, 1); b.taup = shfl_d(v, 2); b.csb2 = shfl_d(v, 3);
   b.a = exp(x);
   const double ia = fast_rcp(b.a), ia2 = ia * ia, iH = fast_rcp(b.H), iH2 = iH * iH;
@@ -706,23 +708,33 @@ __device__ __forceinline__ void factor_reg(const Lane& ln, const BgS& b, double 
     const double bd = top ? btr : 1.0 + dtau;
     const double up = top ? 0.0 : f.hk * (1.0 - RLc(l));
     const double lo = top ? -f.hk : -f.hk * RLc(l);
-    const double ibl = act ? fast_rcp(bd - (up * ibn) * lo_next) : 0.0;
+    const double rc = fast_rcp(bd - (up * ibn) * lo_next);      // unconditional (>= 1 on every lane): no branch around it
+    const double ibl = act ? rc : 0.0;
     f.ibv(l) = ibl; ibn = ibl; lo_next = act ? lo : 0.0;
   }
   const bool live = kind != CH_IDLE;
   const double up2 = f.hk * (1.0 - RLc(2)), up1 = f.hk * (1.0 - RLc(1)), up0 = f.hk;
   const double lo2 = -f.hk * RLc(2), lo1 = -f.hk * RLc(1);
-  const double ib2 = live ? fast_rcp((1.0 + dtau) - (up2 * ibn) * lo_next) : 0.0;
+  const double rc2 = fast_rcp((1.0 + dtau) - (up2 * ibn) * lo_next);
+  const double ib2 = live ? rc2 : 0.0;
   const double m1 = up1 * ib2;
-  const double ib1 = live ? fast_rcp((1.0 + dtau) - m1 * lo2) : 0.0;
+  const double rc1 = fast_rcp((1.0 + dtau) - m1 * lo2);
+  const double ib1 = live ? rc1 : 0.0;
   const double m0 = up0 * ib1;
-  const double ib0 = live ? fast_rcp((1.0 + (kind == CH_P ? dtau : 0.0)) - m0 * lo1) : 0.0;
+  const double rc0 = fast_rcp((1.0 + (kind == CH_P ? dtau : 0.0)) - m0 * lo1);
+  const double ib0 = live ? rc0 : 0.0;
   f.ibv(2) = ib2; f.ibv(1) = ib1; f.ibv(0) = ib0; f.lo1 = lo1; f.lo2 = lo2;
+  // coupling of rows 0..2 to y = (Phi', Psi, Pi, v_b), by selects (no divergent branches)
   double C0[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0};
-  if (kind == CH_M) { C0[0] = h * ln.df0; C1[1] = -f.hkap * (1.0 / 3.0) * b.eq * ln.df0; }
-  else if (kind == CH_T) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); C1[3] = h * b.taup * (1.0 / 3.0); C2[2] = -h * b.taup * 0.1; }
-  else if (kind == CH_P) { C0[2] = -h * b.taup * 0.5; C2[2] = -h * b.taup * 0.1; }
-  else if (kind == CH_N) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); }
+  {
+    const bool isM = kind == CH_M, isT = kind == CH_T, isP = kind == CH_P, isTN = isT || kind == CH_N;
+    const double htp = h * b.taup;
+    C0[0] = isM ? h * ln.df0 : (isTN ? -h : 0.0);
+    C1[1] = isM ? -f.hkap * (1.0 / 3.0) * b.eq * ln.df0 : (isTN ? f.hkap * (1.0 / 3.0) : 0.0);
+    C1[3] = isT ? htp * (1.0 / 3.0) : 0.0;
+    C2[2] = (isT || isP) ? -htp * 0.1 : 0.0;
+    C0[2] = isP ? -htp * 0.5 : 0.0;
+  }
   double be0[4], be1[4], be2[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
@@ -875,11 +887,14 @@ __device__ __forceinline__ void rt_factor_down(const Lane& ln, const BgS& b, dou
   const double up2 = top2 ? 0.0 : f.hk * (1.0 - RLc(2)), up1 = f.hk * (1.0 - RLc(1)), up0 = f.hk;
   const double lo2 = top2 ? -f.hk : -f.hk * RLc(2), lo1 = -f.hk * RLc(1);
   const double mm2 = up2 * ibn;
-  const double ib2 = live ? fast_rcp((top2 ? f.btr : 1.0 + dtau) - mm2 * lo_next) : 0.0;
+  const double rc2 = fast_rcp((top2 ? f.btr : 1.0 + dtau) - mm2 * lo_next);
+  const double ib2 = live ? rc2 : 0.0;
   const double m1 = up1 * ib2;
-  const double ib1 = live ? fast_rcp((1.0 + dtau) - m1 * lo2) : 0.0;
+  const double rc1 = fast_rcp((1.0 + dtau) - m1 * lo2);
+  const double ib1 = live ? rc1 : 0.0;
   const double m0 = up0 * ib1;
-  const double ib0 = live ? fast_rcp((1.0 + (kind == CH_P ? dtau : 0.0)) - m0 * lo1) : 0.0;
+  const double rc0 = fast_rcp((1.0 + (kind == CH_P ? dtau : 0.0)) - m0 * lo1);
+  const double ib0 = live ? rc0 : 0.0;
   f.lo1 = lo1; f.lo2 = lo2;
   r2 = 0.0; r1 = 0.0; r0 = 0.0;
   if (live) {
@@ -887,11 +902,17 @@ __device__ __forceinline__ void rt_factor_down(const Lane& ln, const BgS& b, dou
     ib[i2] = ib2; ib[i1] = ib1; ib[i0] = ib0;
     r2 = r[i2] - mm2 * rn; r1 = r[i1] - m1 * r2; r0 = r[i0] - m0 * r1;
   }
+  // coupling of rows 0..2 to y = (Phi', Psi, Pi, v_b), by selects (no divergent branches)
   double C0[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0};
-  if (kind == CH_M) { C0[0] = h * ln.df0; C1[1] = -f.hkap * (1.0 / 3.0) * b.eq * ln.df0; }
-  else if (kind == CH_T) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); C1[3] = h * b.taup * (1.0 / 3.0); C2[2] = -h * b.taup * 0.1; }
-  else if (kind == CH_P) { C0[2] = -h * b.taup * 0.5; C2[2] = -h * b.taup * 0.1; }
-  else if (kind == CH_N) { C0[0] = -h; C1[1] = f.hkap * (1.0 / 3.0); }
+  {
+    const bool isM = kind == CH_M, isT = kind == CH_T, isP = kind == CH_P, isTN = isT || kind == CH_N;
+    const double htp = h * b.taup;
+    C0[0] = isM ? h * ln.df0 : (isTN ? -h : 0.0);
+    C1[1] = isM ? -f.hkap * (1.0 / 3.0) * b.eq * ln.df0 : (isTN ? f.hkap * (1.0 / 3.0) : 0.0);
+    C1[3] = isT ? htp * (1.0 / 3.0) : 0.0;
+    C2[2] = (isT || isP) ? -htp * 0.1 : 0.0;
+    C0[2] = isP ? -htp * 0.5 : 0.0;
+  }
   double be0[4], be1[4], be2[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
