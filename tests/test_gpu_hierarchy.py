@@ -119,6 +119,39 @@ def test_other_momentum_grid_and_truncations(gpu_ctx):
         assert np.abs(g["S_T"][i] - r["S_T"][i]).max() < 1e-8 * np.abs(r["S_T"][i]).max()
 
 
+def test_long_chain_path_matches_generic_kernel(cosmo, dev, monkeypatch):
+    """The runtime-truncation path (plin 50/50/20, C4 50/8/10) against the first-generation generic kernel
+    (BOLT_K1_GENERIC=1, read at every launch): identical adaptive step sequences, sources to rounding."""
+    from bolt_b200 import abi
+    ks = np.array([0.5, 20.0, 300.0, 900.0]) * cosmo.bg.H0
+    for trunc, rtol in (((50, 8, 10), 1e-9), ((50, 50, 20), 1e-5)):
+        o = abi.make_opts(*trunc, reltol=rtol, abstol=1e-6, ix_first=1201)
+        monkeypatch.delenv("BOLT_K1_GENERIC", raising=False)
+        a = dev.solve(ks, o, want=("S_T", "S_P", "u_final"))
+        monkeypatch.setenv("BOLT_K1_GENERIC", "1")
+        b = dev.solve(ks, o, want=("S_T", "S_P", "u_final"))
+        monkeypatch.delenv("BOLT_K1_GENERIC", raising=False)
+        assert np.all(a["status"] == 0) and np.array_equal(a["nsteps"], b["nsteps"]) and np.array_equal(a["nreject"], b["nreject"])
+        for i in range(len(ks)):
+            assert np.abs(a["u_final"][i] - b["u_final"][i]).max() < 1e-9 * np.abs(b["u_final"][i]).max()
+            for key in ("S_T", "S_P"):
+                x, y = a[key][i, 1201:-1], b[key][i, 1201:-1]
+                assert np.abs(x - y).max() < 1e-9 * np.abs(y).max()
+
+
+@pytest.mark.parametrize("trunc", [(3, 2, 2), (4, 3, 2), (50, 8, 10)])
+def test_long_chain_path_edge_truncations_match_oracle(cosmo, oracle, dev, trunc):
+    """Shortest chains the runtime-truncation path accepts (l_max = 2: the truncation row is one of the three bottom rows) and
+    very uneven chain lengths, fixed step, against the oracle."""
+    from bolt_b200 import abi
+    o = abi.make_opts(*trunc, fixed_dt=0.01)
+    ks = np.array([2.0, 150.0]) * cosmo.bg.H0
+    g = dev.solve(ks, o, want=("u_hist",)); r = oracle.solve(ks, o, want=("u_hist",))
+    assert np.all(g["status"] == r["status"])
+    for i in range(len(ks)):
+        assert hist_err(g["u_hist"][i], r["u_hist"][i]) < 1e-8
+
+
 def test_unsupported_partial_count_fails_loudly(cosmo, gpu_ctx):
     """nd = 6 (five partials) is not instantiated in this build: the call must fail, never silently drop partials."""
     from bolt_b200 import abi, capi
