@@ -629,10 +629,10 @@ struct BgS {
   double kappa, qe, eq, wPsi, wPhi, cPsi, gPhi, k2, R, Oc_a, Ob_a, iHeta;
 };
 __device__ __forceinline__ void eval_bg_fast(const DevCosmo& c, const Lane& ln, const ModeConst& mc, double x, BgS& b) {
-  const int which[4] = {BOLT_T_H, BOLT_T_eta, BOLT_T_taup, BOLT_T_csb2};
   // every lane evaluates one of the four tables (lane & 3): no divergent branch, the extra loads are broadcasts
+  static_assert(BOLT_T_H == 0 && BOLT_T_eta == 3 && BOLT_T_taup == 6 && BOLT_T_csb2 == 11, "table order");
   const int wl = ln.lane & 3;
-  const int tab = (wl == 0) ? which[0] : (wl == 1) ? which[1] : (wl == 2) ? which[2] : which[3];
+  const int tab = 3 * wl + ((wl == 3) ? 2 : 0);       // = which[wl] without a select chain
   const double v = spline_eval(c.tab[tab], c.n_x, c.x0, c.dx, x);
   b.H = shfl_d(v, 0); b.eta = shfl_d(v, 1); b.taup = shfl_d(v, 2); b.csb2 = shfl_d(v, 3);
   b.a = exp(x);
@@ -1178,7 +1178,8 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
         const int lo_ = ln.base;   // column of the lane inside a row of the interleaved layout
         const bool live = (NCH == 32) || ln.kind != CH_IDLE;    // compact layout: idle lanes own no column and never touch memory
         for (int s = 1; s <= 6; s++) {
-          double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
+          // z slot of this stage: Z1 and Z5 swap physical slots with the step parity, Z2..Z4 sit at slots 3..5
+          double* zout = sm + (size_t)((s == 1) ? (flipU ? 0 : 2) : (s >= 5) ? (flipZ ? 1 : 6) : s + 1) * na;
           if (s <= 5) {
             // branch-free assembly: coefficients of stages >= s are zero.  The right-hand side is parked in the stage's own
             // z slot (not yet written) so that z_s = (U - rhs)/gamma needs no register copy

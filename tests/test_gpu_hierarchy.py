@@ -121,28 +121,43 @@ def test_other_momentum_grid_and_truncations(gpu_ctx):
 
 def test_long_chain_path_matches_generic_kernel(cosmo, dev, monkeypatch):
     """The runtime-truncation path (plin 50/50/20, C4 50/8/10) against the first-generation generic kernel
-    (BOLT_K1_GENERIC=1, read at every launch): identical adaptive step sequences, sources to rounding."""
+    (BOLT_K1_GENERIC=1, read at every launch).  Fixed step: same step sequence by construction, results to rounding.
+    Adaptive: the two kernels round the error norm differently (reciprocal vs division, summation order), so the step
+    sequences may part at a borderline accept/reject; the solutions agree at tolerance level."""
     from bolt_b200 import abi
     ks = np.array([0.5, 20.0, 300.0, 900.0]) * cosmo.bg.H0
-    for trunc, rtol in (((50, 8, 10), 1e-9), ((50, 50, 20), 1e-5)):
-        o = abi.make_opts(*trunc, reltol=rtol, abstol=1e-6, ix_first=1201)
+
+    def both(o):
         monkeypatch.delenv("BOLT_K1_GENERIC", raising=False)
         a = dev.solve(ks, o, want=("S_T", "S_P", "u_final"))
         monkeypatch.setenv("BOLT_K1_GENERIC", "1")
         b = dev.solve(ks, o, want=("S_T", "S_P", "u_final"))
         monkeypatch.delenv("BOLT_K1_GENERIC", raising=False)
-        assert np.all(a["status"] == 0) and np.array_equal(a["nsteps"], b["nsteps"]) and np.array_equal(a["nreject"], b["nreject"])
+        return a, b
+
+    def worst(a, b):
+        w = 0.0
         for i in range(len(ks)):
-            assert np.abs(a["u_final"][i] - b["u_final"][i]).max() < 1e-9 * np.abs(b["u_final"][i]).max()
+            w = max(w, np.abs(a["u_final"][i] - b["u_final"][i]).max() / np.abs(b["u_final"][i]).max())
             for key in ("S_T", "S_P"):
                 x, y = a[key][i, 1201:-1], b[key][i, 1201:-1]
-                assert np.abs(x - y).max() < 1e-9 * np.abs(y).max()
+                w = max(w, np.abs(x - y).max() / np.abs(y).max())
+        return w
+
+    for trunc in ((50, 8, 10), (50, 50, 20)):
+        a, b = both(abi.make_opts(*trunc, fixed_dt=0.01, ix_first=1201))
+        assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["nsteps"], b["nsteps"])
+        assert worst(a, b) < 1e-8
+        a, b = both(abi.make_opts(*trunc, reltol=1e-9, abstol=1e-6, ix_first=1201))
+        assert np.all(a["status"] == 0) and np.all(b["status"] == 0)
+        assert np.abs(a["nsteps"] - b["nsteps"]).max() <= 0.02 * b["nsteps"].max()
+        assert worst(a, b) < 1e-6
 
 
-@pytest.mark.parametrize("trunc", [(3, 2, 2), (4, 3, 2), (50, 8, 10)])
+@pytest.mark.parametrize("trunc", [(3, 3, 3), (4, 3, 5), (50, 8, 10)])
 def test_long_chain_path_edge_truncations_match_oracle(cosmo, oracle, dev, trunc):
-    """Shortest chains the runtime-truncation path accepts (l_max = 2: the truncation row is one of the three bottom rows) and
-    very uneven chain lengths, fixed step, against the oracle."""
+    """Shortest chains the library accepts (l_max = 3, source_function needs Θ₃: the truncation row is the first row above the
+    three bottom rows) and very uneven chain lengths, fixed step, against the oracle."""
     from bolt_b200 import abi
     o = abi.make_opts(*trunc, fixed_dt=0.01)
     ks = np.array([2.0, 150.0]) * cosmo.bg.H0
@@ -150,6 +165,9 @@ def test_long_chain_path_edge_truncations_match_oracle(cosmo, oracle, dev, trunc
     assert np.all(g["status"] == r["status"])
     for i in range(len(ks)):
         assert hist_err(g["u_hist"][i], r["u_hist"][i]) < 1e-8
+    from bolt_b200.capi import BoltError
+    with pytest.raises(BoltError):            # l_max < 3 is refused, not silently mis-solved
+        dev.solve(ks, abi.make_opts(3, 2, 3, fixed_dt=0.01), want=("u_hist",))
 
 
 def test_unsupported_partial_count_fails_loudly(cosmo, gpu_ctx):
