@@ -140,7 +140,7 @@ def gradient_arm(ctx, ells):
 
 def plin_arm(ctx, hcosmo, dc):
     """BASELINE configs[1]: linear matter P(k) via plin with massive neutrinos, 500 log-spaced k-modes, the reference's plin
-    defaults l_gamma = l_nu = 50, l_mnu = 20 (state n = 473), reltol 1e-5 (src/spectra.jl:163-164).  Generic K1 path."""
+    defaults l_gamma = l_nu = 50, l_mnu = 20 (state n = 473), reltol 1e-5 (src/spectra.jl:163-164).  Runtime-truncation K1 path."""
     import bolt_b200 as B
     from bolt_b200 import abi
     bg = hcosmo["bg"]
@@ -150,6 +150,23 @@ def plin_arm(ctx, hcosmo, dc):
         t0 = time.perf_counter(); pk, st, ns = dc.plin(ks, o); dt = time.perf_counter() - t0
     return {"workload": "plin, 500 log10_k modes (10 H0 .. 5000 H0), n = 473, reltol 1e-5", "ms": 1e3 * dt, "kmode_solves_per_s": len(ks) / dt,
             "hierarchy_ms": ctx.timing()["hierarchy_ms"], "ode_steps_per_solve": float(ns.mean()), "failed_modes": int((st != 0).sum())}
+
+
+def batch_arm(ctx, hcos, dcs, ells, ncos=4):
+    """SURVEY 8d C5 (emulator / MCMC batches): the same C3-value workload through bolt_spectra_batch, ncos cosmologies per call --
+    all ncos x 2000 hierarchy solves in ONE launch, so the tail of the persistent kernel is paid once per batch."""
+    from bolt_b200 import abi, capi
+    sel = [i % 2 for i in range(ncos)]
+    ks = np.stack([hcos[j]["k"] for j in sel])
+    kmin = np.array([hcos[j]["kd"][0] for j in sel]); kmax = np.array([hcos[j]["kd"][1] for j in sel])
+    o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL)
+    for rep in range(2):
+        t0 = time.perf_counter()
+        out = capi.spectra_batch(ctx, [dcs[j] for j in sel], ks, o, ells, kmin, kmax, hcos[0]["kd"][2], hcos[0]["ix_start"])
+        dt = time.perf_counter() - t0
+    return {"workload": f"C3-value x {ncos} cosmologies per call (bolt_spectra_batch)", "ms_per_call": 1e3 * dt, "ms_per_cosmology": 1e3 * dt / ncos,
+            "kmode_solves_per_s": ncos * NK / dt, "spectra_per_s": ncos / dt, "hierarchy_ms": ctx.timing()["hierarchy_ms"],
+            "failed_modes": int((out[3] != 0).sum())}
 
 
 def main():
@@ -300,10 +317,17 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_sample(hcos[0])
             line["cpu_baseline"] = cb
+        # the extra arms must never cost the headline line
+        def guarded(fn, *a):
+            try:
+                return fn(*a)
+            except Exception as e:          # noqa: BLE001 -- reported in the JSON line instead of aborting the benchmark
+                return {"error": f"{type(e).__name__}: {e}"[:300]}
         if not args.no_gradients and world == 1:
-            line["gradients"] = gradient_arm(ctx, ells)
+            line["gradients"] = guarded(gradient_arm, ctx, ells)
         if world == 1:
-            line["plin"] = plin_arm(ctx, hcos[0], dcs[0])
+            line["plin"] = guarded(plin_arm, ctx, hcos[0], dcs[0])
+            line["batch"] = guarded(batch_arm, ctx, hcos, dcs, ells)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

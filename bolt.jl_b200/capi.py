@@ -15,7 +15,7 @@ _LIB = None
 
 EXPORTS = ["bolt_abi_version", "bolt_init", "bolt_finalize", "bolt_last_error", "bolt_last_timing",
            "bolt_cosmo_upload", "bolt_cosmo_free", "bolt_state_dim", "bolt_solve", "bolt_project",
-           "bolt_spectra", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak", "bolt_set_bessel_xmax"]
+           "bolt_spectra", "bolt_spectra_batch", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak", "bolt_set_bessel_xmax"]
 
 
 class BoltError(RuntimeError):
@@ -43,6 +43,8 @@ def lib():
                                    dp, dp, dp]
         L.bolt_spectra.argtypes = [vp, vp, dp, C.c_int, C.POINTER(abi.Opts), ip, C.c_int, C.c_double, C.c_double,
                                    C.c_int, C.c_int, dp, dp, dp, ip, lp]
+        L.bolt_spectra_batch.argtypes = [vp, C.POINTER(vp), C.c_int, dp, C.c_int, C.POINTER(abi.Opts), ip, C.c_int, dp, dp,
+                                         C.c_int, C.c_int, dp, dp, dp, ip, lp]
         L.bolt_plin.argtypes = [vp, vp, dp, C.c_int, C.POINTER(abi.Opts), dp, ip, lp]
         L.bolt_fp64_peak.argtypes = [vp, dp]
         L.bolt_set_bessel_xmax.argtypes = [vp, C.c_double]
@@ -91,6 +93,23 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def spectra_batch(ctx, dcs, ks, opts, ells, kd_min, kd_max, n_kd, ix_start):
+    """bolt_spectra_batch: dcs = list of DeviceCosmo on ctx, ks = [ncos][nk], kd_min/kd_max = [ncos].
+    Returns tt, te, ee [ncos][nell], status, nsteps [ncos][nk]."""
+    ncos = len(dcs)
+    ks = np.ascontiguousarray(ks, dtype=np.float64); assert ks.shape[0] == ncos
+    ells = np.ascontiguousarray(ells, dtype=np.int32)
+    kd_min = np.ascontiguousarray(kd_min, dtype=np.float64); kd_max = np.ascontiguousarray(kd_max, dtype=np.float64)
+    nk, nell = ks.shape[1], len(ells)
+    tt, te, ee = np.zeros((ncos, nell)), np.zeros((ncos, nell)), np.zeros((ncos, nell))
+    st = np.zeros((ncos, nk), dtype=np.int32); ns = np.zeros((ncos, nk), dtype=np.int64)
+    handles = (C.c_void_p * ncos)(*[d._h for d in dcs])
+    ctx.check(lib().bolt_spectra_batch(ctx._h, handles, ncos, abi.ptr(ks), nk, C.byref(opts), abi.ptr(ells, abi.c_int32_p), nell,
+                                       abi.ptr(kd_min), abi.ptr(kd_max), n_kd, ix_start, abi.ptr(tt), abi.ptr(te), abi.ptr(ee),
+                                       abi.ptr(st, abi.c_int32_p), abi.ptr(ns, abi.c_int64_p)))
+    return tt, te, ee, st, ns
 
 
 class DeviceCosmo:

@@ -9,6 +9,7 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#include <memory>
 
 #ifndef K1_NCH
 #define K1_NCH 32
@@ -698,6 +699,66 @@ int bolt_spectra(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, co
   if (nsteps) CUDA_OK(cudaMemcpyAsync(nsteps, d_ns.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return collect_timing(ctx);
+}
+
+int bolt_spectra_batch(bolt_ctx* ctx, const bolt_cosmo* const* cosmos, int ncos, const double* k, int nk, const bolt_opts* o,
+                       const int32_t* ell, int nell, const double* kd_min, const double* kd_max, int n_kd, int ix_start,
+                       double* cl_tt, double* cl_te, double* cl_ee, int32_t* status, int64_t* nsteps) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (!cosmos || ncos < 1 || ncos > BOLT_MAX_BATCH || !k || nk < 2 || !ell || nell < 1 || !kd_min || !kd_max)
+    return fail(ctx, BOLT_ERR_ARG, "bad arguments (1 <= ncos <= BOLT_MAX_BATCH)");
+  for (int i = 0; i < ncos; i++) {
+    const bolt_cosmo* c = cosmos[i];
+    if (!c) return fail(ctx, BOLT_ERR_ARG, "null cosmology in batch");
+    if (c->h.nd != 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "bolt_spectra_batch is value-only (nd = 1): call bolt_spectra per cosmology for partials");
+    if (c->h.n_x != cosmos[0]->h.n_x || c->h.nq != cosmos[0]->h.nq || c->h.x0 != cosmos[0]->h.x0 || c->h.dx != cosmos[0]->h.dx)
+      return fail(ctx, BOLT_ERR_ARG, "cosmologies of a batch must share x_grid and nq");
+    int rc = check_opts(ctx, c, o); if (rc) return rc;
+  }
+  CUDA_OK(cudaSetDevice(ctx->device));
+  reset_timing(ctx);
+  CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const bolt_cosmo* c0 = cosmos[0];
+  const int n_x = c0->h.n_x, nkt = ncos * nk;
+  DevBuf<double> d_k, d_ST, d_SP, d_cl; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns; DevBuf<const DevCosmo*> d_list;
+  int rc = upload_k_sorted(ctx, k, nkt, d_k, d_order); if (rc) return rc;      // ONE queue over all cosmologies, longest solves first
+  {
+    std::vector<const DevCosmo*> list(ncos);
+    for (int i = 0; i < ncos; i++) list[i] = cosmos[i]->d;
+    CUDA_OK(d_list.alloc(ctx, ncos));
+    CUDA_OK(cudaMemcpyAsync(d_list.p, list.data(), ncos * sizeof(const DevCosmo*), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));   // `list` is a local
+  }
+  CUDA_OK(d_ST.alloc(ctx, (size_t)nkt * n_x)); CUDA_OK(d_SP.alloc(ctx, (size_t)nkt * n_x));
+  CUDA_OK(d_status.alloc(ctx, nkt)); CUDA_OK(d_ns.alloc(ctx, nkt)); CUDA_OK(d_cl.alloc(ctx, (size_t)3 * nell * ncos));
+  bolt_opts oo = *o;
+  oo.ix_first = std::max(oo.ix_first, ix_start);
+  // K1: one persistent launch over ncos x nk modes (mode ik belongs to cosmology ik / nk): the tail of the launch is paid once
+  rc = launch_hierarchy(ctx, d_list.p, c0->h.nq, 0, 1, nullptr, nk, d_k.p, d_order.p, nkt, &oo, d_ST.p, d_SP.p, nullptr, nullptr,
+                        d_status.p, d_ns.p, nullptr);
+  if (rc) return rc;
+  // K2 per cosmology (the j_l table range k_max eta_0 differs); tables on the second stream as in bolt_spectra
+  // All tables are allocated and enqueued BEFORE the first projection: project_device returns its temporaries to the pool
+  // while its kernels are still in flight on the main stream, and a table built on the second stream must never land in one.
+  std::vector<std::unique_ptr<BesselTabs>> tabs;
+  for (int i = 0; i < ncos; i++) {
+    tabs.emplace_back(new BesselTabs());
+    rc = bessel_prepare(ctx, cosmos[i], ell, nell, kd_max[i], ctx->stream2, *tabs.back()); if (rc) return rc;
+  }
+  for (int i = 0; i < ncos; i++) {
+    rc = project_device(ctx, cosmos[i], d_ST.p + (size_t)i * nk * n_x, d_SP.p + (size_t)i * nk * n_x, d_k.p + (size_t)i * nk, nk, *tabs[i],
+                        nell, kd_min[i], kd_max[i], n_kd, ix_start, d_cl.p + (size_t)i * 3 * nell);
+    if (rc) return rc;
+    double* base = d_cl.p + (size_t)i * 3 * nell;
+    if (cl_tt) CUDA_OK(cudaMemcpyAsync(cl_tt + (size_t)i * nell, base, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cl_te) CUDA_OK(cudaMemcpyAsync(cl_te + (size_t)i * nell, base + nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cl_ee) CUDA_OK(cudaMemcpyAsync(cl_ee + (size_t)i * nell, base + 2 * nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (status) CUDA_OK(cudaMemcpyAsync(status, d_status.p, nkt * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nsteps) CUDA_OK(cudaMemcpyAsync(nsteps, d_ns.p, nkt * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));     // the tables in `tabs` are released after the last projection has run
   return collect_timing(ctx);
 }
 

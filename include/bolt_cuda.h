@@ -121,6 +121,17 @@ int  bolt_spectra(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, c
                   double* cl_tt, double* cl_te, double* cl_ee,
                   int32_t* status, int64_t* nsteps);
 
+/* bolt_spectra for a batch of cosmologies (the emulator / MCMC workload: SURVEY 8d C5; the reference maps source_grid over
+ * parameter sets one at a time).  All ncos x nk hierarchy solves share ONE launch (one work queue, longest solves first), so
+ * the low-occupancy tail of the persistent kernel is paid once per batch instead of once per cosmology; the projections run
+ * per cosmology.  k is [ncos][nk] (each cosmology its own grid), kd_min/kd_max are [ncos]; cl_* are [ncos][nell], status and
+ * nsteps [ncos][nk].  Value-only (nd = 1), the cosmologies must share x_grid and nq, 1 <= ncos <= BOLT_MAX_BATCH. */
+#define BOLT_MAX_BATCH 16
+int  bolt_spectra_batch(bolt_ctx* ctx, const bolt_cosmo* const* cosmos, int ncos, const double* k, int nk,
+                        const bolt_opts* o, const int32_t* ell, int nell, const double* kd_min, const double* kd_max,
+                        int n_kd, int ix_start, double* cl_tt, double* cl_te, double* cl_ee,
+                        int32_t* status, int64_t* nsteps);
+
 /* plin for a vector of k (src/spectra.jl:163-198; x = 0). pk is [nk][nd]. */
 int  bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
                double* pk, int32_t* status, int64_t* nsteps);

@@ -134,3 +134,27 @@ def test_c4_style_high_lgamma(cosmo, dev):
     hi = dev.spectra(ks, abi.make_opts(50, 8, 10, reltol=1e-11, abstol=1e-6), ells, *args)
     assert np.all(hi[3] == 0) and abi.state_dim(50, 8, 10, 15) == 281
     assert np.abs(hi[0] / lo[0] - 1).max() < 0.03 and np.abs(hi[2] / lo[2] - 1).max() < 0.06
+
+
+def test_spectra_batch_equals_per_cosmology_calls(cosmo, cosmo_nonu, gpu_ctx):
+    """bolt_spectra_batch (one K1 launch over all cosmologies) returns exactly what bolt_spectra returns per cosmology:
+    a k-mode's solve does not depend on what else is in the queue, and K2 runs per cosmology either way."""
+    import bolt_b200 as B
+    from bolt_b200 import abi, capi
+    cs = [cosmo, cosmo_nonu, cosmo]
+    dcs = [capi.DeviceCosmo(gpu_ctx, c.hc) for c in cs]
+    nk = 48
+    ks = np.stack([B.quadratic_k(0.1 * c.bg.H0, 1000 * c.bg.H0, nk) for c in cs])
+    ells = np.array([2, 10, 50, 200, 600, 1200, 2000], dtype=np.int32)
+    o = abi.make_opts(8, 8, 10, reltol=1e-7, abstol=1e-6)
+    kmin = np.array([0.01 * c.bg.H0 for c in cs]); kmax = np.array([1000 * c.bg.H0 for c in cs])
+    ix0 = int(np.argmax(cosmo.bg.x_grid > -8))
+    tt, te, ee, st, ns = capi.spectra_batch(gpu_ctx, dcs, ks, o, ells, kmin, kmax, 800, ix0)
+    assert tt.shape == (3, len(ells)) and st.shape == (3, nk)
+    for i, dc in enumerate(dcs):
+        t1, e1, p1, s1, n1 = dc.spectra(ks[i], o, ells, kmin[i], kmax[i], 800, ix0)
+        assert np.array_equal(st[i], s1) and np.array_equal(ns[i], n1)
+        assert np.array_equal(tt[i], t1) and np.array_equal(te[i], e1) and np.array_equal(ee[i], p1)
+    assert not np.array_equal(tt[0], tt[1]) and np.array_equal(tt[0], tt[2])
+    with pytest.raises(capi.BoltError):
+        capi.spectra_batch(gpu_ctx, dcs * 6, np.tile(ks, (6, 1)), o, ells, np.tile(kmin, 6), np.tile(kmax, 6), 800, ix0)   # > BOLT_MAX_BATCH
