@@ -601,7 +601,7 @@ struct Trunc {
   static constexpr int MAXLEN = (NQ_ > 0) ? MAXL + 1 : 0;     // 0 = generic (runtime) kernel
   // row stride of the interleaved shared-memory layout: one private column per LANE (not per chain), so idle lanes and the
   // padded rows of short chains can run the unguarded, branch-free code on zeros
-  static constexpr int NCH = NCH_;     // 32 in the value kernel; NQ+4 (compact + one shared all-zero column for the idle lanes) in the dual kernel
+  static constexpr int NCH = NCH_;     // NQ+4: compact + one shared all-zero column for the idle lanes (both register kernels); 32: private column per lane
   static constexpr bool RT = false;
   // row l is the truncation row / an existing row of the lane's chain
   static __device__ __forceinline__ bool top(int kind, int l) {
@@ -1176,7 +1176,11 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
         BgS bf;
         double rr[MAXLEN], r5[5];
         const int lo_ = ln.base;   // column of the lane inside a row of the interleaved layout
-        const bool live = (NCH == 32) || ln.kind != CH_IDLE;    // compact layout: idle lanes own no column and never touch memory
+        // NCH = 32: a private column per lane; NCH = NQ + 4: compact layout + one shared all-zero column for the idle lanes.  Either
+        // way no access needs an idle-lane guard.  The compact layout also lets the stage assembly run FLAT over the whole state
+        // (7 lane-strided elements per lane instead of the lane's 11 rows + 5 scalars).
+        constexpr bool FLAT = (NCH == TR::NQ + 4);
+        const bool live = (NCH == 32) || FLAT || ln.kind != CH_IDLE;
         for (int s = 1; s <= 6; s++) {
           // z slot of this stage: Z1 and Z5 swap physical slots with the step parity, Z2..Z4 sit at slots 3..5
           double* zout = sm + (size_t)((s == 1) ? (flipU ? 0 : 2) : (s >= 5) ? (flipZ ? 1 : 6) : s + 1) * na;
@@ -1184,20 +1188,35 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
             // branch-free assembly: coefficients of stages >= s are zero.  The right-hand side is parked in the stage's own
             // z slot (not yet written) so that z_s = (U - rhs)/gamma needs no register copy
             const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
+            if constexpr (FLAT) {
+              constexpr int NFLAT = MAXLEN * NCH + 5;
 #pragma unroll
-            for (int l = 0; l < MAXLEN; l++) {
-              const int idx = lo_ + l * NCH;      // padded rows / idle lanes hold zeros
-              double v = 0.0;
-              if (live) { v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx]; zout[idx] = v; }
-              rr[l] = v;
-            }
+              for (int t = 0; t < (NFLAT + 31) / 32; t++) {
+                const int i = ln.lane + 32 * t;
+                if (i < NFLAT) zout[i] = U[i] + a0 * Z0[i] + a1 * Z1[i] + a2 * Z2[i] + a3 * Z3[i] + a4 * Z4[i];
+              }
+              eval_bg_fast(c, ln, mc, x + KC_C[s] * dt, bf);
+              __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 5; j++) {
-              const int idx = ln.iS + j;
-              const double v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
-              r5[j] = v; zout[idx] = v;
+              for (int l = 0; l < MAXLEN; l++) rr[l] = zout[lo_ + l * NCH];
+#pragma unroll
+              for (int j = 0; j < 5; j++) r5[j] = zout[ln.iS + j];
+            } else {
+#pragma unroll
+              for (int l = 0; l < MAXLEN; l++) {
+                const int idx = lo_ + l * NCH;      // padded rows / idle lanes hold zeros
+                double v = 0.0;
+                if (live) { v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx]; zout[idx] = v; }
+                rr[l] = v;
+              }
+#pragma unroll
+              for (int j = 0; j < 5; j++) {
+                const int idx = ln.iS + j;
+                const double v = U[idx] + a0 * Z0[idx] + a1 * Z1[idx] + a2 * Z2[idx] + a3 * Z3[idx] + a4 * Z4[idx];
+                r5[j] = v; zout[idx] = v;
+              }
+              eval_bg_fast(c, ln, mc, x + KC_C[s] * dt, bf);
             }
-            eval_bg_fast(c, ln, mc, x + KC_C[s] * dt, bf);
             rsa_flag |= (ln.k * bf.eta > 240.0) && (-bf.taup * bf.H > 100.0 * bf.eta);
             factor_reg<TR>(ln, bf, KC_GAMMA * dt, f);
           } else {
@@ -1230,8 +1249,20 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
             for (int l = 0; l < MAXLEN; l++) if (live) { const int idx = lo_ + l * NCH; zout[idx] = (rr[l] - zout[idx]) * (1.0 / KC_GAMMA); }
             // every lane holds identical scalars and stores them itself (same value, same address): a lane later reads
             // back what it wrote, so no warp-level synchronisation is needed anywhere in the stage loop
+            if constexpr (FLAT) {
+              // the parked scalars were written by one lane each: every lane reads, the warp converges, every lane writes the same
+              // value; the closing barrier also publishes the rows to the next stage's flat pass
+              double zz[5];
 #pragma unroll
-            for (int j = 0; j < 5; j++) { const int idx = ln.iS + j; zout[idx] = (r5[j] - zout[idx]) * (1.0 / KC_GAMMA); }
+              for (int j = 0; j < 5; j++) zz[j] = (r5[j] - zout[ln.iS + j]) * (1.0 / KC_GAMMA);
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 5; j++) zout[ln.iS + j] = zz[j];
+              __syncwarp();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 5; j++) { const int idx = ln.iS + j; zout[idx] = (r5[j] - zout[idx]) * (1.0 / KC_GAMMA); }
+            }
           }
         }
         __syncwarp();     // the sampling / rotation code below reads other lanes' data
