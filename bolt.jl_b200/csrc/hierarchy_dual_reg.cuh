@@ -50,7 +50,7 @@ __device__ __forceinline__ Dual<NP> g_row_reg(const Lane& ln, const BgD<NP>& b, 
 }
 
 template <class TR, int NP> __host__ __device__ constexpr size_t k1_dualreg_smem_doubles() {
-  return (size_t)7 * (1 + NP) * (TR::MAXLEN * TR::NCH + 8) + k1_extra_doubles<TR>();   // + factor scratch
+  return (size_t)7 * (1 + NP) * (TR::MAXLEN * TR::NCH + 8) + k1_extra_doubles<TR>() + (TR::MAXLEN * TR::NCH + 8);   // + factor scratch + rhs scratch
 }
 
 template <class TR, int NP>
@@ -160,6 +160,8 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
 
       RegFactor<TR> f;
       f.fs = sm + (size_t)7 * (1 + NP) * (TR::MAXLEN * TR::NCH + 8) + ln.lane;
+      double* const scr2 = sm + (size_t)7 * (1 + NP) * (TR::MAXLEN * TR::NCH + 8) + k1_extra_doubles<TR>();   // right-hand side of a partial system
+      constexpr int NFLAT = MAXLEN * NCH + 5;     // the elementwise passes run flat over the state (7 lane-strided elements per lane)
       BgS bf;
       double rr[MAXLEN], r5[5];
       bool accept = true; double EEst = 0.0, q11 = 0.0;
@@ -179,10 +181,13 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
         // every right-hand side is formed ONCE and parked in the stage's own (not yet written) z slot, so that
         // z = (solution - rhs)/gamma needs neither a register copy nor a second pass over the six state arrays
 #pragma unroll
-        for (int l = 0; l < MAXLEN; l++) { double v = 0.0; if (live) { const int idx = lo_ + l * NCH; v = rhs_at(0, idx); zout.p[idx] = v; } rr[l] = v; }
-#pragma unroll
-        for (int j = 0; j < 5; j++) { const int idx = ln.iS + j; const double v = rhs_at(0, idx); r5[j] = v; zout.p[idx] = v; }
+        for (int t = 0; t < (NFLAT + 31) / 32; t++) { const int i = ln.lane + 32 * t; if (i < NFLAT) zout.p[i] = rhs_at(0, i); }
         eval_bg_fast(c, ln, mc, xs, bf);
+        __syncwarp();
+#pragma unroll
+        for (int l = 0; l < MAXLEN; l++) rr[l] = zout.p[lo_ + l * NCH];
+#pragma unroll
+        for (int j = 0; j < 5; j++) r5[j] = zout.p[ln.iS + j];
         rsa_flag |= (ln.k * bf.eta > 240.0) && (-bf.taup * bf.H > 100.0 * bf.eta);
         factor_reg<TR>(ln, bf, h, f);
         solve_reg<TR>(ln, bf, f, rr, r5);          // rr, r5 = stage value U
@@ -226,20 +231,23 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
 #pragma unroll
           for (int j = 0; j < 5; j++) zout.p[ln.iS + j] = zz[j];
         }
+        __syncwarp();       // h G_j (written by the chain owners) is read flat below
         // ---- partials: W S_j = r_j + h G_j with the factorisation in hand ----
 #pragma unroll 1
         for (int j = 1; j <= NP; j++) {
           double* zj = zout.p + (size_t)j * na;
           // system right-hand side r_j + h G_j (h G_j waits in zj); r_j is parked in zj for the stage increment
 #pragma unroll
-          for (int l = 0; l < MAXLEN; l++) { double v = 0.0; if (live) { const int idx = lo_ + l * NCH; const double rj = rhs_at(j, idx); v = rj + zj[idx]; zj[idx] = rj; } rr[l] = v; }
-          // (the five scalars are shared by all lanes: every lane reads, the warp converges, then every lane writes the same value)
-          double rj5[5];
-#pragma unroll
-          for (int q = 0; q < 5; q++) { const int idx = ln.iS + q; rj5[q] = rhs_at(j, idx); r5[q] = rj5[q] + zj[idx]; }
+          for (int t = 0; t < (NFLAT + 31) / 32; t++) {
+            const int i = ln.lane + 32 * t;
+            if (i < NFLAT) { const double rj = rhs_at(j, i); scr2[i] = rj + zj[i]; zj[i] = rj; }
+          }
           __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 5; q++) zj[ln.iS + q] = rj5[q];
+          for (int l = 0; l < MAXLEN; l++) rr[l] = scr2[lo_ + l * NCH];
+#pragma unroll
+          for (int q = 0; q < 5; q++) r5[q] = scr2[ln.iS + q];
+          double rj5[5];
           solve_reg<TR>(ln, bf, f, rr, r5);
 #pragma unroll
           for (int l = 0; l < MAXLEN; l++) if (live) { const int idx = lo_ + l * NCH; zj[idx] = (rr[l] - zj[idx]) * (1.0 / KC_GAMMA); }
@@ -260,10 +268,10 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
             Z1.p[o] = U.p[o] + b0 * Z0.p[o] + KC_A[5][2] * Z2.p[o] + KC_A[5][3] * Z3.p[o] + KC_A[5][4] * Z4.p[o] + KC_GAMMA * Z5.p[o];
           }
         };
+        __syncwarp();       // the last stage's increments were written by the chain owners
 #pragma unroll
-        for (int l = 0; l < MAXLEN; l++) if (live) unew(lo_ + l * NCH);
-#pragma unroll
-        for (int j = 0; j < 5; j++) unew(ln.iS + j);
+        for (int t = 0; t < (NFLAT + 31) / 32; t++) { const int i = ln.lane + 32 * t; if (i < NFLAT) unew(i); }
+        __syncwarp();
       }
       if (!fixed) {
         // error norm over value and partials (DiffEqBase semantics, see hierarchy_dual.cuh), each component's estimate
