@@ -127,4 +127,25 @@ function plin(ks::AbstractVector, 𝕡::AbstractCosmoParams{T}, bg, ih, n_q=15, 
     unflat(T, pk, nd)
 end
 
+"""TT/TE/EE for a batch of parameter sets (Float64 only): one bolt_spectra_batch call -- all hierarchy solves in ONE launch.
+`batch` is a vector of (𝕡, bg, ih); every cosmology gets `quadratic_k(0.1H₀, 1000H₀, nk)` as in examples/basic_usage.jl."""
+function spectra_batch(ℓ⃗, batch::AbstractVector; nk=2000, ℓᵧ=8, reltol=1e-11, dev=Device())
+    ctx = context(dev.ordinal); ncos = length(batch); nℓ = length(ℓ⃗)
+    cs = [upload(ctx, 𝕡, bg, ih)[1] for (𝕡, bg, ih) in batch]
+    H₀ = [Float64(bg.H₀) for (_, bg, _) in batch]
+    k = reduce(hcat, [collect(quadratic_k(0.1h0, 1000h0, nk)) for h0 in H₀])          # [nk, ncos] = C [ncos][nk]
+    kd_min = 0.01 .* H₀; kd_max = 1000 .* H₀
+    bg1 = batch[1][2]; ix_start = findfirst(bg1.x_grid .> -8) - 1
+    tt = zeros(Float64, nℓ, ncos); te = similar(tt); ee = similar(tt)
+    status = zeros(Int32, nk, ncos); nsteps = zeros(Int64, nk, ncos)
+    o = Opts(ℓᵧ, 8, 10, 0, reltol, 1e-6, 0.0, 0, 0, 0)
+    GC.@preserve cs k tt te ee status nsteps check(ctx, ccall((:bolt_spectra_batch, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Float64}, Cint, Ref{Opts}, Ptr{Int32}, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Cint,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}),
+        ctx, cs, ncos, k, nk, o, Int32.(collect(ℓ⃗)), nℓ, kd_min, kd_max, 5000, ix_start, tt, te, ee, status, nsteps))
+    foreach(c -> ccall((:bolt_cosmo_free, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx, c), cs)
+    any(status .∉ Ref((0, 4))) && @warn "some k-modes did not finish" count(status .∉ Ref((0, 4)))
+    tt, te, ee
+end
+
 end # module
