@@ -122,6 +122,9 @@ int init_constants(bolt_ctx* ctx) {
   double rl[MAX_L + 1];
   for (int l = 0; l <= MAX_L; l++) rl[l] = (double)l / (double)(2 * l + 1);
   CUDA_OK(cudaMemcpyToSymbol(c_rl, rl, sizeof(rl)));
+  double rl1[MAX_L + 1];
+  for (int l = 0; l <= MAX_L; l++) rl1[l] = 1.0 - rl[l];
+  CUDA_OK(cudaMemcpyToSymbol(c_rl1, rl1, sizeof(rl1)));
   g_const_init[ctx->device] = true;
   return BOLT_OK;
 }

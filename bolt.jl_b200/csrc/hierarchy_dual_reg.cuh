@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
 #pragma unroll
         for (int j = 0; j < 5; j++) r5[j] = zout.p[ln.iS + j];
         rsa_flag |= (ln.k * bf.eta > 240.0) && (-bf.taup * bf.H > 100.0 * bf.eta);
-        factor_reg<TR>(ln, bf, h, f);
-        solve_reg<TR>(ln, bf, f, rr, r5);          // rr, r5 = stage value U
+        factor_reg<TR, false>(ln, bf, h, f);
+        solve_reg<TR, false>(ln, bf, f, rr, r5);          // rr, r5 = stage value U
         // ---- G = (dA/dp) U in dual arithmetic on the plain stage value; h G_j -> zout_j ----
         eval_bg_d_stage<NP>(c, ln, xs, tv, bd);
         {
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
 #pragma unroll
           for (int q = 0; q < 5; q++) r5[q] = scr2[ln.iS + q];
           double rj5[5];
-          solve_reg<TR>(ln, bf, f, rr, r5);
+          solve_reg<TR, false>(ln, bf, f, rr, r5);
 #pragma unroll
           for (int l = 0; l < MAXLEN; l++) if (live) { const int idx = lo_ + l * NCH; zj[idx] = (rr[l] - zj[idx]) * (1.0 / KC_GAMMA); }
 #pragma unroll
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
           for (int l = 0; l < MAXLEN; l++) rr[l] = live ? err_at(j, lo_ + l * NCH) : 0.0;
 #pragma unroll
           for (int q = 0; q < 5; q++) r5[q] = err_at(j, ln.iS + q);
-          solve_reg<TR>(ln, bf, f, rr, r5);
+          solve_reg<TR, false>(ln, bf, f, rr, r5);
 #pragma unroll
           for (int l = 0; l < MAXLEN; l++) { const double q = rr[l] * isc[l]; ssum += q * q; }
           if (ln.lane == 0) {

@@ -52,6 +52,7 @@ struct SolveParams {
 };
 
 __constant__ double c_rl[MAX_L + 1];   // l/(2l+1)
+__constant__ double c_rl1[MAX_L + 1];  // 1 - l/(2l+1)
 
 // KenCarp4 implicit tableau (Kennedy & Carpenter 2003, ARK4(3)6L[2]SA-ESDIRK); SURVEY 8c.
 #define KC_GAMMA 0.25
@@ -692,7 +693,12 @@ __device__ __forceinline__ void ge4(const double (&Min)[4][4], const double (&rh
   y[0] = (a[0][4] - a[0][1] * y[1] - a[0][2] * y[2] - a[0][3] * y[3]) * fast_rcp(a[0][0]);
 }
 
-template <class TR>
+// l/(2l+1) and 1 - l/(2l+1) for a compile-time l: as constant-bank operands (CB: no UMOV pair per use, -4 % in the value kernel)
+// or as immediates (the kernel with partials: the constant-bank form costs it registers and spills)
+template <bool CB> __device__ __forceinline__ double rl_of(int l) { return CB ? c_rl[l] : RLc(l); }
+template <bool CB> __device__ __forceinline__ double rl1_of(int l) { return CB ? c_rl1[l] : 1.0 - RLc(l); }
+
+template <class TR, bool CB = true>
 __device__ __forceinline__ void factor_reg(const Lane& ln, const BgS& b, double h, RegFactor<TR>& f) {
   constexpr int MAXLEN = TR::MAXLEN;
   const int kind = ln.kind;
@@ -706,15 +712,15 @@ __device__ __forceinline__ void factor_reg(const Lane& ln, const BgS& b, double 
   for (int l = MAXLEN - 1; l >= 3; l--) {
     const bool act = TR::act(kind, l), top = TR::top(kind, l);
     const double bd = top ? btr : 1.0 + dtau;
-    const double up = top ? 0.0 : f.hk * (1.0 - RLc(l));
-    const double lo = top ? -f.hk : -f.hk * RLc(l);
+    const double up = top ? 0.0 : f.hk * rl1_of<CB>(l);
+    const double lo = top ? -f.hk : -f.hk * rl_of<CB>(l);
     const double rc = fast_rcp(bd - (up * ibn) * lo_next);      // unconditional (>= 1 on every lane): no branch around it
     const double ibl = act ? rc : 0.0;
     f.ibv(l) = ibl; ibn = ibl; lo_next = act ? lo : 0.0;
   }
   const bool live = kind != CH_IDLE;
-  const double up2 = f.hk * (1.0 - RLc(2)), up1 = f.hk * (1.0 - RLc(1)), up0 = f.hk;
-  const double lo2 = -f.hk * RLc(2), lo1 = -f.hk * RLc(1);
+  const double up2 = f.hk * rl1_of<CB>(2), up1 = f.hk * rl1_of<CB>(1), up0 = f.hk;
+  const double lo2 = -f.hk * rl_of<CB>(2), lo1 = -f.hk * rl_of<CB>(1);
   const double rc2 = fast_rcp((1.0 + dtau) - (up2 * ibn) * lo_next);
   const double ib2 = live ? rc2 : 0.0;
   const double m1 = up1 * ib2;
@@ -772,7 +778,7 @@ __device__ __forceinline__ void factor_reg(const Lane& ln, const BgS& b, double 
 
 // Solve W U = r for the lane's chain in rr[] (registers, overwritten by U) and the 5 scalars in r5[] (every lane
 // holds the same copy).
-template <class TR>
+template <class TR, bool CB = true>
 __device__ __forceinline__ void solve_reg(const Lane& ln, const BgS& b, const RegFactor<TR>& f,
                                           double (&rr)[TR::MAXLEN > 0 ? TR::MAXLEN : 1], double (&r5)[5]) {
   constexpr int MAXLEN = TR::MAXLEN;
@@ -780,13 +786,13 @@ __device__ __forceinline__ void solve_reg(const Lane& ln, const BgS& b, const Re
   double ibn = 0.0, rn = 0.0;
 #pragma unroll
   for (int l = MAXLEN - 1; l >= 3; l--) {
-    const double up = TR::top(kind, l) ? 0.0 : f.hk * (1.0 - RLc(l));
+    const double up = TR::top(kind, l) ? 0.0 : f.hk * rl1_of<CB>(l);
     const double v = rr[l] - (up * ibn) * rn;
     rr[l] = v; rn = v; ibn = f.ibv(l);
   }
-  const double r2 = rr[2] - (f.hk * (1.0 - RLc(2)) * ibn) * rn;
+  const double r2 = rr[2] - (f.hk * rl1_of<CB>(2) * ibn) * rn;
   const double ib0 = f.ibv(0), ib1 = f.ibv(1), ib2 = f.ibv(2);
-  const double r1 = rr[1] - (f.hk * (1.0 - RLc(1)) * ib2) * r2;
+  const double r1 = rr[1] - (f.hk * rl1_of<CB>(1) * ib2) * r2;
   const double r0 = rr[0] - (f.hk * ib1) * r1;
   const double a0 = r0 * ib0, a1 = (r1 - f.lo1 * a0) * ib1, a2 = (r2 - f.lo2 * a1) * ib2;
   const int lT = ln.nq, lP = ln.nq + 1;
@@ -816,7 +822,7 @@ __device__ __forceinline__ void solve_reg(const Lane& ln, const BgS& b, const Re
   double Up = U2;
 #pragma unroll
   for (int l = 3; l < MAXLEN; l++) {
-    const double lo = TR::top(kind, l) ? -f.hk : -f.hk * RLc(l);
+    const double lo = TR::top(kind, l) ? -f.hk : -f.hk * rl_of<CB>(l);
     const double U = (rr[l] - lo * Up) * f.ibv(l);
     rr[l] = U; Up = U;
   }
