@@ -288,8 +288,8 @@ def main():
                 "unit": "TFLOP/s", "frac": fl / (k1_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
                 "traffic": 1.16e6, "traffic_note": "dram bytes read+write per launch from profiles/r1_k1_hierarchy.md (ncu --set full): K1 is not HBM bound",
                 "peak_source": "DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
-                "note": "algorithmic flop = accepted steps x (182 n + 3300), n = 197 (DESIGN.md); ncu: FP64 pipe active 25% of cycles, "
-                        "issue slots 31% -- dependency-latency and instruction-fetch bound at 8 warps/SM (profiles/README.md)"}
+                "note": "algorithmic flop = accepted steps x (182 n + 3300), n = 197 (DESIGN.md); ncu: FP64 pipe active 26% of cycles, "
+                        "issue slots 36% -- issue- and instruction-fetch bound at 8 warps/SM (profiles/r1_k1_hierarchy_v6.md)"}
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
