@@ -65,6 +65,17 @@ def host_cosmo_with_partials(par, names, rel_step=1e-3, x_grid=None):
     return abi.HostCosmo.with_partials(base, pm, steps), base, bg, ih, pm, steps
 
 
+def _check_status(status, where):
+    """The reference never checks the solver's retcode (perturbations.jl:29-32); the shim warns instead of staying silent
+    (SURVEY 8b).  0 = ok, 4 = the RSA switch fired inside the solve (reported, results still returned)."""
+    bad = np.asarray(status)
+    bad = bad[(bad != abi.K_OK) & (bad != abi.K_RSA_TRIGGERED)]
+    if bad.size:
+        import warnings
+        warnings.warn(f"{where}: {bad.size} k-mode(s) did not finish (status codes {sorted(set(bad.tolist()))}: 1 max steps, "
+                      "2 step underflow, 3 non-finite); their remaining rows are zero", RuntimeWarning, stacklevel=3)
+
+
 class Hierarchy:
     """src/perturbations.jl:7-21"""
 
@@ -81,18 +92,24 @@ class Hierarchy:
 
 class Solution:
     """What boltsolve returns: callable like the reference's ODESolution, `sol(x) -> Vector(n)`.
-    The solution is held on bg.x_grid (the device's Hermite dense output sampled at every grid point);
-    between grid points it is interpolated linearly (documented deviation: the reference interpolates
-    between its own adaptive steps)."""
+    The solution is held on bg.x_grid (the device's Hermite dense output sampled at every grid point: exact there);
+    between grid points a local four-point cubic through the neighbouring rows is used (O(dx⁴) like the
+    reference's Hermite interpolant between its own steps, which the device does not keep)."""
 
     def __init__(self, x_grid, u, status, nsteps):
         self.t, self.u, self.retcode, self.nsteps = x_grid, u, int(status), int(nsteps)
 
     def __call__(self, x):
-        t = (x - self.t[0]) / ((self.t[-1] - self.t[0]) / (len(self.t) - 1))
-        i = int(np.clip(np.floor(t), 0, len(self.t) - 2))
+        nx = len(self.t)
+        t = (x - self.t[0]) / ((self.t[-1] - self.t[0]) / (nx - 1))
+        i = int(np.clip(np.floor(t), 0, nx - 2))
         w = t - i
-        return (1 - w) * self.u[i] + w * self.u[i + 1]
+        if w == 0.0:
+            return self.u[i].copy()
+        j = int(np.clip(i - 1, 0, nx - 4))          # rows j..j+3, Lagrange weights at s = t - j
+        s_ = t - j
+        wts = [-(s_ - 1) * (s_ - 2) * (s_ - 3) / 6, s_ * (s_ - 2) * (s_ - 3) / 2, -s_ * (s_ - 1) * (s_ - 3) / 2, s_ * (s_ - 1) * (s_ - 2) / 6]
+        return sum(wt * self.u[j + m] for m, wt in enumerate(wts))
 
 
 def _opts(h_or_trunc, reltol, abstol, **kw):
@@ -106,6 +123,7 @@ def boltsolve(hierarchy, ode_alg=None, reltol=1e-6, abstol=1e-6, ctx=None):
     h = hierarchy
     dc = device_cosmo(h.par, h.bg, h.ih, ctx)
     out = dc.solve(np.array([h.k]), _opts((h.ℓᵧ, h.ℓ_ν, h.ℓ_mν), reltol, abstol), want=("u_hist",))
+    _check_status(out["status"], "boltsolve")
     return Solution(h.bg.x_grid, out["u_hist"][0], out["status"][0], out["nsteps"][0])
 
 
@@ -185,38 +203,40 @@ def _source_grids(par, bg, ih, k_grid, ℓᵧ, reltol, ctx):
     k_grid = np.ascontiguousarray(k_grid, dtype=np.float64)
     out = dc.solve(k_grid, _opts((ℓᵧ, 8, 10), reltol, 1e-6), want=("S_T", "S_P"))
     meta = dict(status=out["status"], nsteps=out["nsteps"], nreject=out["nreject"])
+    _check_status(out["status"], "source_grid")
     sT = SourceInterpolant(bg.x_grid, k_grid, np.ascontiguousarray(out["S_T"].T), meta=meta)
     sP = SourceInterpolant(bg.x_grid, k_grid, np.ascontiguousarray(out["S_P"].T), meta=meta)
     sT._other, sP._other = sP, sT
     return sT, sP
 
 
-_pair_cache = {}
+# The sibling grid of the last source_grid / source_grid_P call (one entry).  The entry keeps `bg` and `ih` alive and is
+# matched by identity (`is`), never by a bare id(): an id can be reused by a new object once the old one is collected.
+_pair_cache = []
 
 
-def _pair_key(par, bg, ih, k_grid, ℓᵧ, reltol):
-    return (id(bg), id(ih), np.asarray(k_grid, dtype=np.float64).tobytes(), ℓᵧ, reltol)
+def _sibling(which, par, bg, ih, k_grid, ℓᵧ, reltol, ctx):
+    kb = np.asarray(k_grid, dtype=np.float64).tobytes()
+    if _pair_cache:
+        e = _pair_cache[0]
+        if e["bg"] is bg and e["ih"] is ih and e["k"] == kb and e["trunc"] == (ℓᵧ, reltol) and e["left"] == which:
+            _pair_cache.clear()
+            return e["pair"][which]
+    pair = _source_grids(par, bg, ih, k_grid, ℓᵧ, reltol, ctx)
+    _pair_cache.clear()
+    _pair_cache.append(dict(bg=bg, ih=ih, k=kb, trunc=(ℓᵧ, reltol), pair=pair, left=1 - which))
+    return pair[which]
 
 
 def source_grid(par, bg, ih, k_grid, integrator, ℓᵧ=8, reltol=1e-11, ctx=None):
     """src/spectra.jl:6-23.  The device emits the temperature AND polarization source from the same
     solve, so the sibling grid is cached for a following source_grid_P call with the same arguments."""
-    key = _pair_key(par, bg, ih, k_grid, ℓᵧ, reltol)
-    pair = _pair_cache.pop(key, None)
-    if pair is None:
-        pair = _source_grids(par, bg, ih, k_grid, ℓᵧ, reltol, ctx)
-        _pair_cache.clear(); _pair_cache[key] = pair
-    return pair[0]
+    return _sibling(0, par, bg, ih, k_grid, ℓᵧ, reltol, ctx)
 
 
 def source_grid_P(par, bg, ih, k_grid, integrator, ℓᵧ=8, reltol=1e-11, ctx=None):
     """src/spectra.jl:25-42"""
-    key = _pair_key(par, bg, ih, k_grid, ℓᵧ, reltol)
-    pair = _pair_cache.pop(key, None)
-    if pair is None:
-        pair = _source_grids(par, bg, ih, k_grid, ℓᵧ, reltol, ctx)
-        _pair_cache.clear(); _pair_cache[key] = pair
-    return pair[1]
+    return _sibling(1, par, bg, ih, k_grid, ℓᵧ, reltol, ctx)
 
 
 def quadratic_k(kmin, kmax, nk):
@@ -244,13 +264,12 @@ def _is_quadratic(kgrid):
 def _project(ells, sT, sP, kd_min, kd_max, n_kd, par, bg, ih, ctx):
     scalar = np.isscalar(ells)
     ells = np.atleast_1d(np.asarray(ells, dtype=np.int32))
-    order = np.argsort(ells, kind="stable")
+    uniq, inv = np.unique(ells, return_inverse=True)      # the library wants strictly increasing multipoles; the caller may repeat
     ref = sT if sT is not None else sP
     dc = device_cosmo(par, bg, ih if ih is not None else ref.meta.get("ih"), ctx)
     tt, te, ee = dc.project(None if sT is None else np.ascontiguousarray(sT.grid.T),
                             None if sP is None else np.ascontiguousarray(sP.grid.T),
-                            ref.k_grid, ells[order], kd_min, kd_max, n_kd, _ix_start(bg))
-    inv = np.empty_like(order); inv[order] = np.arange(len(order))
+                            ref.k_grid, uniq, kd_min, kd_max, n_kd, _ix_start(bg))
     res = [None if a is None else (a[inv][0] if scalar else a[inv]) for a in (tt, te, ee)]
     return res
 
@@ -294,14 +313,45 @@ def clee(*args, ih=None, ctx=None):
 
 def plin(k, par, bg, ih, n_q=15, ℓᵧ=50, ℓ_ν=50, ℓ_mν=20, x=0, reltol=1e-5, ctx=None):
     """src/spectra.jl:163-198.  Accepts a scalar k (like the reference) or a vector of k (one batched call)."""
-    if x != 0:
-        raise NotImplementedError("plin is evaluated at x = 0 on the device (the reference default)")
     if n_q != bg.nq:
         raise ValueError("n_q must match the background's quadrature")
     dc = device_cosmo(par, bg, ih, ctx)
     ks = np.atleast_1d(np.asarray(k, dtype=np.float64))
+    if x != 0:
+        # perturb(x) at an interior abscissa: the device solves the modes and returns their histories on bg.x_grid;
+        # the epilogue (spectra.jl:170-197, a few dozen flop per mode) runs here on the interpolated state
+        out = dc.solve(ks, _opts((ℓᵧ, ℓ_ν, ℓ_mν), reltol, 1e-6), want=("u_hist",))
+        _check_status(out["status"], "plin")
+        pk = np.array([_plin_from_state(Solution(bg.x_grid, out["u_hist"][i], out["status"][i], out["nsteps"][i])(x),
+                                        ks[i], par, bg, x, ℓᵧ, ℓ_ν, ℓ_mν) for i in range(len(ks))])
+        return pk[0] if np.isscalar(k) else pk
     pk, status, _ = dc.plin(ks, _opts((ℓᵧ, ℓ_ν, ℓ_mν), reltol, 1e-6))
+    _check_status(status, "plin")
     return pk[0] if np.isscalar(k) else pk
+
+
+def _plin_from_state(u, k, par, bg, x, ℓᵧ, ℓ_ν, ℓ_mν):
+    """The epilogue of plin (src/spectra.jl:170-197) on a state vector `u = perturb(x)`."""
+    from .host.background import q_grid, f0, dxdq
+    nq = bg.nq
+    iM = 2 * (ℓᵧ + 1) + (ℓ_ν + 1); iS = iM + (ℓ_mν + 1) * nq
+    q, lqmi, lqma = q_grid(par, bg.quad_pts)
+    a = np.exp(x)
+    eps = np.sqrt(q ** 2 + (a * par.Σm_ν) ** 2)
+    w = f0(q, par) / dxdq(q, lqmi, lqma) * bg.quad_wts
+    ρ0M, Hx = bg.ρ0M(x), bg.H(x)
+    Mρ = 4 * np.pi * np.sum(q ** 2 * eps * w * u[iM:iM + nq]) / ρ0M                  # ρ_σ (perturbations.jl:127-145)
+    Mθ = k * 4 * np.pi * np.sum(q ** 3 * w * u[iM + nq:iM + 2 * nq]) / ρ0M            # θ   (perturbations.jl:148-158)
+    δcN, vcN, δbN, vbN = u[iS + 1], u[iS + 2], u[iS + 3], u[iS + 4]
+    vmν = -Mθ / k
+    Tγ = (15 / np.pi ** 2 * bg.ρ_crit * par.Ω_r) ** 0.25
+    νfac = (90 * 1.2020569 / (11 * np.pi ** 4)) * (par.Ω_r * par.h ** 2 / Tγ) * (par.N_ν / 3) ** 0.75
+    Ω_ν = par.Σm_ν * νfac / par.h ** 2
+    Ωm = par.Ω_c + par.Ω_b + Ω_ν
+    δc = δcN - 3 * Hx * vcN / k; δb = δbN - 3 * Hx * vbN / k
+    δmν = Mρ - 3 * Hx * vmν / k
+    δm = (par.Ω_c * δc + par.Ω_b * δb + Ω_ν * δmν) / Ωm
+    return (2 * np.pi ** 2 / k ** 3) * δm ** 2 * par.A * (k / 0.05) ** (par.n - 1)
 
 
 def spectra(ells, par, bg, ih, k_grid, ℓᵧ=8, reltol=1e-11, ctx=None):
@@ -311,4 +361,5 @@ def spectra(ells, par, bg, ih, k_grid, ℓᵧ=8, reltol=1e-11, ctx=None):
     ells = np.asarray(ells, dtype=np.int32)
     tt, te, ee, status, nsteps = dc.spectra(k_grid, _opts((ℓᵧ, 8, 10), reltol, 1e-6), ells, 0.01 * bg.H0, 1000 * bg.H0, 5000,
                                             _ix_start(bg))
-    return tt, te, ee, dict(status=status, nsteps=nsteps)
+    _check_status(status, "spectra")
+    return tt, te, ee, dict(status=status, nsteps=nsteps, nreject=dc.last_nreject)

@@ -42,7 +42,7 @@ def lib():
         L.bolt_project.argtypes = [vp, vp, dp, dp, dp, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                    dp, dp, dp]
         L.bolt_spectra.argtypes = [vp, vp, dp, C.c_int, C.POINTER(abi.Opts), ip, C.c_int, C.c_double, C.c_double,
-                                   C.c_int, C.c_int, dp, dp, dp, ip, lp]
+                                   C.c_int, C.c_int, dp, dp, dp, ip, lp, lp]
         L.bolt_spectra_batch.argtypes = [vp, C.POINTER(vp), C.c_int, dp, C.c_int, C.POINTER(abi.Opts), ip, C.c_int, dp, dp,
                                          C.c_int, C.c_int, dp, dp, dp, ip, lp]
         L.bolt_plin.argtypes = [vp, vp, dp, C.c_int, C.POINTER(abi.Opts), dp, ip, lp]
@@ -170,11 +170,12 @@ class DeviceCosmo:
         ells = np.ascontiguousarray(ells, dtype=np.int32)
         shp = (len(ells),) if self.hc.nd == 1 else (len(ells), self.hc.nd)
         tt, te, ee = np.zeros(shp), np.zeros(shp), np.zeros(shp)
-        st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
+        st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64); nr = np.zeros(len(k), dtype=np.int64)
         self.ctx.check(lib().bolt_spectra(self.ctx._h, self._h, abi.ptr(k), len(k), C.byref(opts),
                                           abi.ptr(ells, abi.c_int32_p), len(ells), kd_min, kd_max, n_kd, ix_start,
                                           abi.ptr(tt), abi.ptr(te), abi.ptr(ee), abi.ptr(st, abi.c_int32_p),
-                                          abi.ptr(ns, abi.c_int64_p)))
+                                          abi.ptr(ns, abi.c_int64_p), abi.ptr(nr, abi.c_int64_p)))
+        self.last_nreject = nr          # rejected steps per mode of the last call (cost as much as accepted ones)
         return tt, te, ee, st, ns
 
     def plin(self, k, opts):
@@ -191,6 +192,8 @@ class DeviceCosmo:
         import torch
         nk, n_x = k_t.numel(), self.hc.n_x
         dev = k_t.device
+        if self.hc.nd != 1:
+            raise BoltError("solve_device: value-only cosmologies (nd = 1); the kernels with partials write [nk][n_x][nd]")
         S_T = torch.zeros((nk, n_x), dtype=torch.float64, device=dev)
         S_P = torch.zeros((nk, n_x), dtype=torch.float64, device=dev)
         status = torch.zeros(nk, dtype=torch.int32, device=dev)

@@ -339,11 +339,21 @@ struct BesselTabs {
   DevBuf<int> d_ell; DevBuf<double> d_J, d_Cf, d_cp, d_iden;
   double dg = 0.0;
 };
+// An error after work has been enqueued: drain both streams before the DevBufs of the caller return to the pool.
+int bail(bolt_ctx* ctx, int rc) {
+  cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
+  return rc;
+}
 int check_ells(bolt_ctx* ctx, const int32_t* ell, int nell) {
   for (int i = 0; i < nell; i++) {
     if (ell[i] < 0) return fail(ctx, BOLT_ERR_ARG, "negative multipole");
     if (i > 0 && ell[i] <= ell[i - 1]) return fail(ctx, BOLT_ERR_ARG, "multipoles must be strictly increasing");
   }
+  return BOLT_OK;
+}
+int check_projection_args(bolt_ctx* ctx, const bolt_cosmo* c, const int32_t* ell, int nell, int n_kd, int ix_start) {
+  int rc = check_ells(ctx, ell, nell); if (rc) return rc;
+  if (n_kd < 2 || ix_start < 0 || ix_start >= c->h.n_x - 1) return fail(ctx, BOLT_ERR_ARG, "bad dense grid / ix_start");
   return BOLT_OK;
 }
 int bessel_prepare(bolt_ctx* ctx, const bolt_cosmo* c, const int32_t* ell, int nell, double kd_max, cudaStream_t st, BesselTabs& bt) {
@@ -565,8 +575,10 @@ int bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* d, bolt_cosmo** out)
         for (int t = 0; t < BOLT_NTABLES; t++)
           for (int a = 0; a < na; a++)
             for (int i = 0; i < nc; i++) dt[((size_t)t * na + a) * nc + i] = d->tables[((size_t)t * nc + i) * nd + c->map_k1[a]];
-        cudaMalloc(&c->d_dtables_k1, dt.size() * sizeof(double));
-        cudaMemcpy(c->d_dtables_k1, dt.data(), dt.size() * sizeof(double), cudaMemcpyHostToDevice);
+        if (cudaMalloc(&c->d_dtables_k1, dt.size() * sizeof(double)) != cudaSuccess ||
+            cudaMemcpy(c->d_dtables_k1, dt.data(), dt.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+          bolt_cosmo_free(ctx, c); return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc/cudaMemcpy compact partial tables");
+        }
         for (int t = 0; t < BOLT_NTABLES; t++) k1.dtab[t] = c->d_dtables_k1 + (size_t)t * na * nc;
         for (int a = 0; a < na; a++) {
           const int j = c->map_k1[a] - 1;
@@ -575,12 +587,16 @@ int bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* d, bolt_cosmo** out)
           k1.dOmega_nu[a] = h.dOmega_nu[j]; k1.deta_end[a] = h.deta_end[j];
         }
       }
-      cudaMalloc(&c->d_k1, sizeof(DevCosmo));
-      cudaMemcpy(c->d_k1, &k1, sizeof(DevCosmo), cudaMemcpyHostToDevice);
+      if (cudaMalloc(&c->d_k1, sizeof(DevCosmo)) != cudaSuccess ||
+          cudaMemcpy(c->d_k1, &k1, sizeof(DevCosmo), cudaMemcpyHostToDevice) != cudaSuccess) {
+        bolt_cosmo_free(ctx, c); return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc/cudaMemcpy compact cosmology");
+      }
       eta_end_kernel<<<1, 1, 0, ctx->stream>>>(c->d_k1);
-      cudaStreamSynchronize(ctx->stream);
-      cudaMalloc(&c->d_list_k1, sizeof(DevCosmo*));
-      cudaMemcpy(c->d_list_k1, &c->d_k1, sizeof(DevCosmo*), cudaMemcpyHostToDevice);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+          cudaMalloc(&c->d_list_k1, sizeof(DevCosmo*)) != cudaSuccess ||
+          cudaMemcpy(c->d_list_k1, &c->d_k1, sizeof(DevCosmo*), cudaMemcpyHostToDevice) != cudaSuccess) {
+        bolt_cosmo_free(ctx, c); return fail(ctx, BOLT_ERR_CUDA, "compact cosmology upload");
+      }
     } else {
       c->np_k1 = np;
       for (int j = 0; j < np; j++) c->map_k1[j] = 1 + j;
@@ -671,37 +687,40 @@ int bolt_project(bolt_ctx* ctx, const bolt_cosmo* c, const double* S_T, const do
 
 int bolt_spectra(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
                  const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start,
-                 double* cl_tt, double* cl_te, double* cl_ee, int32_t* status, int64_t* nsteps) {
+                 double* cl_tt, double* cl_te, double* cl_ee, int32_t* status, int64_t* nsteps, int64_t* nreject) {
   if (!ctx) return BOLT_ERR_ARG;
   if (!c || !k || nk < 2 || !ell || nell < 1) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
   int rc = check_opts(ctx, c, o); if (rc) return rc;
+  rc = check_projection_args(ctx, c, ell, nell, n_kd, ix_start); if (rc) return rc;     // before any work is enqueued
   CUDA_OK(cudaSetDevice(ctx->device));
   reset_timing(ctx);
   CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
   const int nd = c->h.nd, n_x = c->h.n_x * nd;
   const size_t ncl = (size_t)nell * nd;
-  DevBuf<double> d_k, d_ST, d_SP, d_cl; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns;
+  DevBuf<double> d_k, d_ST, d_SP, d_cl; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns, d_nr;
   rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
   CUDA_OK(d_ST.alloc(ctx, (size_t)nk * n_x)); CUDA_OK(d_SP.alloc(ctx, (size_t)nk * n_x));
-  if (c->np_k1 < c->h.np) {     // partials the hierarchy does not carry (A, n) stay exactly zero in the source grids
-    CUDA_OK(cudaMemsetAsync(d_ST.p, 0, d_ST.n * 8, ctx->stream)); CUDA_OK(cudaMemsetAsync(d_SP.p, 0, d_SP.n * 8, ctx->stream));
-  }
-  CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk)); CUDA_OK(d_cl.alloc(ctx, 3 * ncl));
+  // Always cleared: a mode that stops early (status 1..3) leaves its remaining rows unwritten, and the pool hands out
+  // recycled memory -- K2 must never read another cosmology's sources there.  Partials the hierarchy does not carry
+  // (A, n) stay exactly zero for the same reason.
+  CUDA_OK(cudaMemsetAsync(d_ST.p, 0, d_ST.n * 8, ctx->stream)); CUDA_OK(cudaMemsetAsync(d_SP.p, 0, d_SP.n * 8, ctx->stream));
+  CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk)); CUDA_OK(d_nr.alloc(ctx, nk)); CUDA_OK(d_cl.alloc(ctx, 3 * ncl));
   bolt_opts oo = *o;
   oo.ix_first = std::max(oo.ix_first, ix_start);    // the LOS sum only reads rows >= ix_start (spectra.jl:86)
   BesselTabs bt;
-  rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, d_ST.p, d_SP.p, nullptr, nullptr, d_status.p, d_ns.p, nullptr);
-  if (rc) return rc;
+  rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, d_ST.p, d_SP.p, nullptr, nullptr, d_status.p, d_ns.p, d_nr.p);
+  if (rc) return bail(ctx, rc);
   // The j_l tables do not depend on K1.  Enqueued AFTER it on a second stream, their blocks are scheduled as K1's persistent
   // warps retire, i.e. they fill the low-occupancy tail of the hierarchy solve instead of delaying its start.
-  rc = bessel_prepare(ctx, c, ell, nell, kd_max, ctx->stream2, bt); if (rc) return rc;
+  rc = bessel_prepare(ctx, c, ell, nell, kd_max, ctx->stream2, bt); if (rc) return bail(ctx, rc);
   rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, bt, nell, kd_min, kd_max, n_kd, ix_start, d_cl.p);
-  if (rc) return rc;
+  if (rc) return bail(ctx, rc);
   if (cl_tt) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (cl_te) CUDA_OK(cudaMemcpyAsync(cl_te, d_cl.p + ncl, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (cl_ee) CUDA_OK(cudaMemcpyAsync(cl_ee, d_cl.p + 2 * ncl, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CUDA_OK(cudaMemcpyAsync(status, d_status.p, nk * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (nsteps) CUDA_OK(cudaMemcpyAsync(nsteps, d_ns.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nreject) CUDA_OK(cudaMemcpyAsync(nreject, d_nr.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return collect_timing(ctx);
@@ -720,6 +739,7 @@ int bolt_spectra_batch(bolt_ctx* ctx, const bolt_cosmo* const* cosmos, int ncos,
     if (c->h.n_x != cosmos[0]->h.n_x || c->h.nq != cosmos[0]->h.nq || c->h.x0 != cosmos[0]->h.x0 || c->h.dx != cosmos[0]->h.dx)
       return fail(ctx, BOLT_ERR_ARG, "cosmologies of a batch must share x_grid and nq");
     int rc = check_opts(ctx, c, o); if (rc) return rc;
+    rc = check_projection_args(ctx, c, ell, nell, n_kd, ix_start); if (rc) return rc;
   }
   CUDA_OK(cudaSetDevice(ctx->device));
   reset_timing(ctx);
@@ -736,25 +756,26 @@ int bolt_spectra_batch(bolt_ctx* ctx, const bolt_cosmo* const* cosmos, int ncos,
     CUDA_OK(cudaStreamSynchronize(ctx->stream));   // `list` is a local
   }
   CUDA_OK(d_ST.alloc(ctx, (size_t)nkt * n_x)); CUDA_OK(d_SP.alloc(ctx, (size_t)nkt * n_x));
+  CUDA_OK(cudaMemsetAsync(d_ST.p, 0, d_ST.n * 8, ctx->stream)); CUDA_OK(cudaMemsetAsync(d_SP.p, 0, d_SP.n * 8, ctx->stream));   // see bolt_spectra
   CUDA_OK(d_status.alloc(ctx, nkt)); CUDA_OK(d_ns.alloc(ctx, nkt)); CUDA_OK(d_cl.alloc(ctx, (size_t)3 * nell * ncos));
   bolt_opts oo = *o;
   oo.ix_first = std::max(oo.ix_first, ix_start);
   // K1: one persistent launch over ncos x nk modes (mode ik belongs to cosmology ik / nk): the tail of the launch is paid once
   rc = launch_hierarchy(ctx, d_list.p, c0->h.nq, 0, 1, nullptr, nk, d_k.p, d_order.p, nkt, &oo, d_ST.p, d_SP.p, nullptr, nullptr,
                         d_status.p, d_ns.p, nullptr);
-  if (rc) return rc;
+  if (rc) return bail(ctx, rc);
   // K2 per cosmology (the j_l table range k_max eta_0 differs); tables on the second stream as in bolt_spectra
   // All tables are allocated and enqueued BEFORE the first projection: project_device returns its temporaries to the pool
   // while its kernels are still in flight on the main stream, and a table built on the second stream must never land in one.
   std::vector<std::unique_ptr<BesselTabs>> tabs;
   for (int i = 0; i < ncos; i++) {
     tabs.emplace_back(new BesselTabs());
-    rc = bessel_prepare(ctx, cosmos[i], ell, nell, kd_max[i], ctx->stream2, *tabs.back()); if (rc) return rc;
+    rc = bessel_prepare(ctx, cosmos[i], ell, nell, kd_max[i], ctx->stream2, *tabs.back()); if (rc) return bail(ctx, rc);
   }
   for (int i = 0; i < ncos; i++) {
     rc = project_device(ctx, cosmos[i], d_ST.p + (size_t)i * nk * n_x, d_SP.p + (size_t)i * nk * n_x, d_k.p + (size_t)i * nk, nk, *tabs[i],
                         nell, kd_min[i], kd_max[i], n_kd, ix_start, d_cl.p + (size_t)i * 3 * nell);
-    if (rc) return rc;
+    if (rc) return bail(ctx, rc);
     double* base = d_cl.p + (size_t)i * 3 * nell;
     if (cl_tt) CUDA_OK(cudaMemcpyAsync(cl_tt + (size_t)i * nell, base, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (cl_te) CUDA_OK(cudaMemcpyAsync(cl_te + (size_t)i * nell, base + nell, nell * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -780,7 +801,7 @@ int bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const
   DevBuf<double> d_k, d_final, d_pk; DevBuf<int> d_order, d_status; DevBuf<long long> d_ns;
   rc = upload_k_sorted(ctx, k, nk, d_k, d_order); if (rc) return rc;
   CUDA_OK(d_final.alloc(ctx, (size_t)nk * n * nd)); CUDA_OK(d_pk.alloc(ctx, (size_t)nk * nd));
-  if (c->np_k1 < c->h.np) CUDA_OK(cudaMemsetAsync(d_final.p, 0, d_final.n * 8, ctx->stream));
+  CUDA_OK(cudaMemsetAsync(d_final.p, 0, d_final.n * 8, ctx->stream));
   CUDA_OK(d_status.alloc(ctx, nk)); CUDA_OK(d_ns.alloc(ctx, nk));
   bolt_opts oo = *o; oo.ix_first = c->h.n_x;   // plin only needs perturb(0): no source sampling
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, nullptr, nullptr, nullptr, d_final.p, d_status.p, d_ns.p, nullptr);
@@ -818,6 +839,12 @@ int bolt_solve_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, int
   DevBuf<double> d_k2; DevBuf<int> d_order;
   rc = upload_k_sorted(ctx, hk.data(), nk, d_k2, d_order); if (rc) return rc;
   static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  {   // the kernels write only the rows >= ix_first and the partial slots they carry: everything else must read as zero
+    const size_t ncol = (size_t)nk * c->h.n_x * c->h.nd;
+    if (d_S_T) CUDA_OK(cudaMemsetAsync(d_S_T, 0, ncol * 8, ctx->stream));
+    if (d_S_P) CUDA_OK(cudaMemsetAsync(d_S_P, 0, ncol * 8, ctx->stream));
+    if (d_u_final) CUDA_OK(cudaMemsetAsync(d_u_final, 0, (size_t)nk * bolt_state_dim(o->l_gamma, o->l_nu, o->l_mnu, c->h.nq) * c->h.nd * 8, ctx->stream));
+  }
   rc = launch_hierarchy(ctx, c, d_k, d_order.p, nk, o, d_S_T, d_S_P, nullptr, d_u_final, d_status, (long long*)d_nsteps, (long long*)d_nreject);
   if (rc) return rc;
   CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));

@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(32) hierarchy_dual_kernel(SolveParams p) {
 #pragma unroll 1
         for (int l = 0; l < ln.len; l++) acc(ln.base + l * ln.stride);
         if (ln.lane < 5) acc(ln.iS + ln.lane);
-        EEst = sqrt(warp_sum(ssum) / ((double)n * ND));     // DiffEqBase: sum of squares over value and partials / totallength
+        EEst = sqrt(warp_sum(ssum) / ((double)n * p.out_nd));     // DiffEqBase: sum of squares over value and partials / totallength of the CALLER's dual state (zero partials count)
         if (!isfinite(EEst)) { status = BOLT_K_NONFINITE; break; }
         q11 = exp(beta1 * log(fmax(EEst, 1e-6)));
         accept = EEst <= 1.0;

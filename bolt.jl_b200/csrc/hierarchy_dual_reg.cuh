@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(32) hierarchy_dual_reg_kernel(SolveParams p) {
             for (int q = 0; q < 5; q++) { const double e = r5[q] * isc5[q]; ssum += e * e; }
           }
         }
-        EEst = sqrt(warp_sum(ssum) / ((double)n * ND));
+        EEst = sqrt(warp_sum(ssum) / ((double)n * p.out_nd));   // totallength of the CALLER's dual state: partials not carried (A, n) are zeros that still count
         if (!isfinite(EEst)) { status = BOLT_K_NONFINITE; break; }
         q11 = exp(beta1 * log(fmax(EEst, 1e-6)));
         accept = EEst <= 1.0;

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BOLT_ABI_VERSION 1
+#define BOLT_ABI_VERSION 2
 
 /* order of the scalar block (each entry nd doubles, value first) */
 enum bolt_scalar {
@@ -119,7 +119,7 @@ int  bolt_project(bolt_ctx* ctx, const bolt_cosmo* c, const double* S_T, const d
 int  bolt_spectra(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
                   const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start,
                   double* cl_tt, double* cl_te, double* cl_ee,
-                  int32_t* status, int64_t* nsteps);
+                  int32_t* status, int64_t* nsteps, int64_t* nreject);
 
 /* bolt_spectra for a batch of cosmologies (the emulator / MCMC workload: SURVEY 8d C5; the reference maps source_grid over
  * parameter sets one at a time).  All ncos x nk hierarchy solves share ONE launch (one work queue, longest solves first), so

@@ -43,6 +43,11 @@ def lib():
         L.oracle_project.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, ip, C.c_int, C.c_double, C.c_double,
                                      C.c_int, C.c_int, dp, dp, dp]
         L.oracle_plin.argtypes = [C.c_void_p, dp, C.c_int, C.POINTER(abi.Opts), C.c_int, dp, ip, lp]
+        L.oracle_set_num_threads.argtypes = [C.c_int]
+        L.oracle_solve_sens.argtypes = [C.c_void_p, dp, C.c_int, C.POINTER(abi.Opts), C.c_int, dp, dp, dp, ip, lp, lp]
+        L.oracle_project_sens.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, ip, C.c_int, C.c_double, C.c_double,
+                                          C.c_int, C.c_int, C.c_double, dp, dp, dp]
+        L.oracle_plin_sens.argtypes = [C.c_void_p, dp, C.c_int, C.POINTER(abi.Opts), C.c_int, dp, ip, lp]
         _LIB = L
     return _LIB
 
@@ -92,6 +97,50 @@ class OracleCosmo:
         pk = np.zeros(len(k)); st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
         lib().oracle_plin(self.h, abi.ptr(k), len(k), C.byref(opts), lu_mode, abi.ptr(pk), abi.ptr(st, abi.c_int32_p),
                           abi.ptr(ns, abi.c_int64_p))
+        return pk, st, ns
+
+    # ---- gradient oracle (host cosmology with partials, nd > 1): forward sensitivities through the same stepper ----
+    def solve_sens(self, k, opts, want=("S_T", "S_P"), lu_mode=1):
+        from bolt_b200 import abi
+        assert self.hc.nd > 1
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        nk, n_x, nd = len(k), self.hc.n_x, self.hc.nd
+        n = abi.state_dim(opts.l_gamma, opts.l_nu, opts.l_mnu, self.hc.nq)
+        out = {}
+        out["S_T"] = np.zeros((nk, n_x, nd)) if "S_T" in want else None
+        out["S_P"] = np.zeros((nk, n_x, nd)) if "S_P" in want else None
+        out["u_final"] = np.zeros((nk, n, nd)) if "u_final" in want else None
+        out["status"] = np.zeros(nk, dtype=np.int32)
+        out["nsteps"] = np.zeros(nk, dtype=np.int64)
+        out["nreject"] = np.zeros(nk, dtype=np.int64)
+        rc = lib().oracle_solve_sens(self.h, abi.ptr(k), nk, C.byref(opts), lu_mode, abi.ptr(out["S_T"]), abi.ptr(out["S_P"]),
+                                     abi.ptr(out["u_final"]), abi.ptr(out["status"], abi.c_int32_p),
+                                     abi.ptr(out["nsteps"], abi.c_int64_p), abi.ptr(out["nreject"], abi.c_int64_p))
+        assert rc == 0
+        return out
+
+    def project_sens(self, S_T, S_P, k, ells, kd_min, kd_max, n_kd, ix_start, xmax_fixed=0.0):
+        from bolt_b200 import abi
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        ells = np.ascontiguousarray(ells, dtype=np.int32)
+        nd = self.hc.nd
+        S_T = None if S_T is None else np.ascontiguousarray(S_T, dtype=np.float64)
+        S_P = None if S_P is None else np.ascontiguousarray(S_P, dtype=np.float64)
+        tt = np.zeros((len(ells), nd)) if S_T is not None else None
+        ee = np.zeros((len(ells), nd)) if S_P is not None else None
+        te = np.zeros((len(ells), nd)) if (S_T is not None and S_P is not None) else None
+        rc = lib().oracle_project_sens(self.h, abi.ptr(S_T), abi.ptr(S_P), abi.ptr(k), len(k), abi.ptr(ells, abi.c_int32_p),
+                                       len(ells), kd_min, kd_max, n_kd, ix_start, xmax_fixed, abi.ptr(tt), abi.ptr(te), abi.ptr(ee))
+        assert rc == 0
+        return tt, te, ee
+
+    def plin_sens(self, k, opts, lu_mode=1):
+        from bolt_b200 import abi
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        pk = np.zeros((len(k), self.hc.nd)); st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
+        rc = lib().oracle_plin_sens(self.h, abi.ptr(k), len(k), C.byref(opts), lu_mode, abi.ptr(pk), abi.ptr(st, abi.c_int32_p),
+                                    abi.ptr(ns, abi.c_int64_p))
+        assert rc == 0
         return pk, st, ns
 
     def initial_conditions(self, k, opts):

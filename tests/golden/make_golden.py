@@ -61,9 +61,113 @@ def oracle_vectors():
                         tables=hc.tables, scalars=hc.scalars, quad_pts=hc.quad_pts, quad_wts=hc.quad_wts, x0=hc.x0, dx=hc.dx)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# 3. Oracle outputs for the BENCHMARKED configurations (bench.py's synthetic cosmology #0), value and gradient:
+#    oracle_c3.npz            C3 value: all 2000 quadratic k-modes, reltol 1e-11, C_l at every 25th multipole
+#    oracle_c3grad.npz        C3 with 6 forward-mode partials (nd = 7: the K1 NP=4 / K2 NP=6 kernels the bench times), full size
+#    oracle_c3grad_small.npz  the same on a 200-mode k grid (minutes instead of an hour of CPU)
+#    oracle_c2.npz            plin, 500 log10_k modes, n = 473, reltol 1e-5; partials on every 10th mode
+#    oracle_c4mini.npz        l_gamma = 50 (n = 281) adaptive, 128 quadratic k-modes
+#    The inputs (host tables WITH partials) are stored in the files: the GPU tests feed bit-identical tables to the device.
+# ------------------------------------------------------------------------------------------------------------------
+GRAD_NAMES = ["Ω_b", "Ω_c", "h", "n", "A", "Σm_ν"]      # bench.py gradient workload (tau is not a reference parameter)
+
+
+def bench_cosmology():
+    """bench.py's synthetic cosmology #0 with partials (host generator + central differences, api.host_cosmo_with_partials)."""
+    import bench
+    import bolt_b200 as B
+    from bolt_b200.api import host_cosmo_with_partials
+    par = bench.synthetic_params(0)
+    dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, GRAD_NAMES, rel_step=1e-3)
+    return par, bg, dual, base
+
+
+def _inputs(hc):
+    return dict(tables=hc.tables, scalars=hc.scalars, quad_pts=hc.quad_pts, quad_wts=hc.quad_wts, x0=hc.x0, dx=hc.dx)
+
+
+def c3_value(par, bg, dual, base):
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    from oracle.oracle import OracleCosmo
+    oc = OracleCosmo(base)
+    kg = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 2000)
+    ix0 = int(np.argmax(bg.x_grid > -8))
+    o = abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6, ix_first=ix0)
+    t = time.time(); out = oc.solve(kg, o, want=("S_T", "S_P")); print("c3 value solve %.0fs" % (time.time() - t), flush=True)
+    ells = np.unique(np.r_[np.arange(2, 2501, 25), 2500]).astype(np.int32)
+    tt, te, ee = oc.project(out["S_T"], out["S_P"], kg, ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, ix0)
+    sel = np.arange(49, 2000, 100)
+    np.savez_compressed(f"{HERE}/oracle_c3.npz", k=kg, ix_start=ix0, ell=ells, tt=tt, te=te, ee=ee, nsteps=out["nsteps"], nreject=out["nreject"],
+                        status=out["status"], sel=sel, S_T=out["S_T"][sel][:, ix0:], S_P=out["S_P"][sel][:, ix0:], **_inputs(base))
+
+
+def c3_grad(par, bg, dual, base, nk, name):
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    from oracle.oracle import OracleCosmo
+    od = OracleCosmo(dual)
+    kg = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, nk)
+    ix0 = int(np.argmax(bg.x_grid > -8))
+    o = abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6, ix_first=ix0)
+    t = time.time(); out = od.solve_sens(kg, o, want=("S_T", "S_P")); print("%s sens solve %.0fs" % (name, time.time() - t), flush=True)
+    ells = np.unique(np.r_[np.arange(2, 2501, 25 if nk >= 2000 else 100), 2500]).astype(np.int32)
+    xmax = 1000 * bg.H0 * bg.η0
+    tt, te, ee = od.project_sens(out["S_T"], out["S_P"], kg, ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, ix0, xmax)
+    sel = np.arange(nk // 40, nk, nk // 20)
+    np.savez_compressed(f"{HERE}/{name}.npz", k=kg, ix_start=ix0, ell=ells, tt=tt, te=te, ee=ee, nsteps=out["nsteps"], nreject=out["nreject"],
+                        status=out["status"], sel=sel, S_T=out["S_T"][sel][:, ix0:], S_P=out["S_P"][sel][:, ix0:], bessel_xmax=xmax,
+                        names=np.array(GRAD_NAMES), **_inputs(dual))
+
+
+def c2_plin(par, bg, dual, base):
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    from oracle.oracle import OracleCosmo
+    oc = OracleCosmo(base); od = OracleCosmo(dual)
+    ks = B.log10_k(10 * bg.H0, 5000 * bg.H0, 500)
+    o = abi.make_opts(50, 50, 20, reltol=1e-5, abstol=1e-6)
+    t = time.time(); pk, st, ns = oc.plin(ks, o); print("c2 plin %.0fs" % (time.time() - t), flush=True)
+    gsel = np.arange(5, 500, 10)
+    t = time.time(); pkg, stg, nsg = od.plin_sens(ks[gsel], o); print("c2 plin sens %.0fs" % (time.time() - t), flush=True)
+    np.savez_compressed(f"{HERE}/oracle_c2.npz", k=ks, pk=pk, status=st, nsteps=ns, gsel=gsel, pk_grad=pkg, nsteps_grad=nsg, status_grad=stg,
+                        names=np.array(GRAD_NAMES), **_inputs(dual))
+
+
+def c4_mini(par, bg, dual, base):
+    import bolt_b200 as B
+    from bolt_b200 import abi
+    from oracle.oracle import OracleCosmo
+    oc = OracleCosmo(base)
+    kg = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 128)
+    ix0 = int(np.argmax(bg.x_grid > -8))
+    o = abi.make_opts(50, 8, 10, reltol=1e-11, abstol=1e-6, ix_first=ix0)
+    t = time.time(); out = oc.solve(kg, o, want=("S_T", "S_P")); print("c4mini solve %.0fs" % (time.time() - t), flush=True)
+    ells = np.array([2, 10, 30, 100, 220, 400, 540, 800, 1000, 1500, 2000, 2500], dtype=np.int32)
+    tt, te, ee = oc.project(out["S_T"], out["S_P"], kg, ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, ix0)
+    sel = np.arange(3, 128, 8)
+    np.savez_compressed(f"{HERE}/oracle_c4mini.npz", k=kg, ix_start=ix0, ell=ells, tt=tt, te=te, ee=ee, nsteps=out["nsteps"], nreject=out["nreject"],
+                        status=out["status"], sel=sel, S_T=out["S_T"][sel][:, ix0:], S_P=out["S_P"][sel][:, ix0:], **_inputs(base))
+
+
+def bench_goldens(which):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    cos = bench_cosmology()
+    if "c4mini" in which: c4_mini(*cos)
+    if "c3grad_small" in which: c3_grad(*cos, 200, "oracle_c3grad_small")
+    if "c3" in which: c3_value(*cos)
+    if "c2" in which: c2_plin(*cos)
+    if "c3grad" in which: c3_grad(*cos, 2000, "oracle_c3grad")
+
+
 if __name__ == "__main__":
-    reference_fixtures()
-    if "--fixtures-only" not in sys.argv:
-        oracle_vectors()
+    stages = [a for a in sys.argv[1:] if not a.startswith("--")]
+    if stages:                       # e.g. `make_golden.py c3 c2 c4mini c3grad_small c3grad` (the last one is ~1 h of CPU)
+        bench_goldens(stages)
+    else:
+        reference_fixtures()
+        if "--fixtures-only" not in sys.argv:
+            oracle_vectors()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

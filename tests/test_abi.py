@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert {"bolt_init", "bolt_solve", "bolt_project", "bolt_spectra", "bolt_plin", "bolt_cosmo_upload"} <= set(names)
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.bolt_abi_version() == 1
+    assert lib.bolt_abi_version() == 2
     assert lib.bolt_state_dim(8, 8, 10, 15) == 197 and lib.bolt_state_dim(50, 50, 20, 15) == 473
 
 
@@ -68,6 +68,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".jl", ".h")):
                 txt = open(os.path.join(d, f)).read()
                 assert not pat.search(txt), os.path.join(d, f)
-    # and bench.py touches it only inside cpu_sample (the reported CPU baseline / --impl reference arm)
-    bench = open(os.path.join(ROOT, "bench.py")).read()
-    assert bench.count("from oracle.oracle import") == 1 and "def cpu_sample" in bench.split("from oracle.oracle import")[0].splitlines()[-3:][0] or True
+    # and bench.py touches it only inside its CPU-baseline legs: functions named cpu_* (the reported cpu_baseline and the
+    # --impl reference arm both go through them), never at module level or inside the GPU arms
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    found = []
+
+    def visit(node, fn):
+        for ch in ast.iter_child_nodes(node):
+            name = ch.name if isinstance(ch, (ast.FunctionDef, ast.AsyncFunctionDef)) else fn
+            if isinstance(ch, ast.ImportFrom) and (ch.module or "").split(".")[0] == "oracle":
+                found.append(fn)
+            if isinstance(ch, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in ch.names):
+                found.append(fn)
+            visit(ch, name)
+    visit(tree, None)
+    assert found and all(fn is not None and fn.startswith("cpu_") for fn in found), found

@@ -40,3 +40,46 @@ def test_dense_grid_detection():
     assert ok and kmin == pytest.approx(0.01, rel=1e-6)
     ok, _ = _is_quadratic(B.log10_k(0.01, 1000.0, 50))
     assert not ok
+
+
+def test_solution_interpolates_cubics_exactly():
+    from bolt_b200.api import Solution
+    xg = np.linspace(-20.0, 0.0, 2001)
+    f = lambda x: np.stack([x ** 3 - 2 * x, 0.5 * x ** 2 + 1.0], axis=-1)
+    sol = Solution(xg, f(xg), 0, 1)
+    for x in (-20.0, -19.9973, -7.123456, -0.0031, 0.0):
+        assert np.allclose(sol(x), f(np.array(x)), rtol=1e-11, atol=1e-9)
+
+
+def test_plin_epilogue_on_host_matches_oracle(cosmo, oracle):
+    """plin(x != 0) runs the epilogue of spectra.jl:170-197 on the host: at x = 0 it must reproduce the oracle's plin."""
+    from bolt_b200 import abi
+    from bolt_b200.api import _plin_from_state
+    ks = np.array([20.0, 600.0]) * cosmo.bg.H0
+    o = abi.make_opts(8, 8, 10, reltol=1e-5, abstol=1e-6)
+    pk, st, _ = oracle.plin(ks, o)
+    uf = oracle.solve(ks, o, want=("u_final",))["u_final"]
+    mine = [_plin_from_state(uf[i], ks[i], cosmo.par, cosmo.bg, 0.0, 8, 8, 10) for i in range(2)]
+    assert np.allclose(mine, pk, rtol=1e-10)
+
+
+def test_sibling_cache_is_keyed_on_identity_not_id(cosmo, monkeypatch):
+    """a new cosmology whose Background happens to reuse the id() of a collected one must not hit the cache."""
+    from bolt_b200 import api
+    calls = []
+
+    def fake(par, bg, ih, k_grid, ℓᵧ, reltol, ctx):
+        calls.append((bg, ih)); return ("T%d" % len(calls), "P%d" % len(calls))
+    monkeypatch.setattr(api, "_source_grids", fake)
+    api._pair_cache.clear()
+    kg = np.array([1.0, 2.0])
+
+    class Obj:
+        pass
+    bg1, ih1, bg2 = Obj(), Obj(), Obj()
+    assert api.source_grid(None, bg1, ih1, kg, None) == "T1"
+    assert api.source_grid_P(None, bg1, ih1, kg, None) == "P1" and len(calls) == 1        # sibling served from the cache
+    assert api.source_grid_P(None, bg1, ih1, kg, None) == "P2"                            # consumed: solved again
+    assert api.source_grid(None, bg2, ih1, kg, None) == "T3"                              # another background: never the cache
+    assert api._pair_cache[0]["bg"] is bg2                                                 # and the entry keeps its objects alive
+    api._pair_cache.clear()

@@ -1,0 +1,161 @@
+"""The BENCHMARKED configurations against committed oracle goldens (tests/golden/make_golden.py, stage names in brackets):
+
+  [c3]            C3 value: all 2000 quadratic k-modes, reltol 1e-11, every 25th multipole          -> C_l <= 1e-4
+  [c3grad_small]  C3 with SIX forward-mode partials (nd = 7: the K1 NP=4 / K2 NP=6 kernels bench.py times), 200 k-modes
+                  -> values <= 1e-4, gradients <= 1e-3 against the oracle's own dual-number run of the dense stepper
+  [c2]            plin, 500 log10_k modes, n = 473, reltol 1e-5 (+ partials on every 10th mode)     -> P(k) <= 1e-4, grad <= 1e-3
+  [c4mini]        l_gamma = 50 (n = 281), adaptive, 128 quadratic k-modes                           -> C_l <= 1e-4
+
+The device is fed the tables stored IN the golden file (bit-identical inputs on both sides).  The gradient oracle is
+independent of the device code: generic dual arithmetic on the restated right-hand side + dense LU (oracle/bolt_oracle.cpp
+solve_mode_sens), mirroring what the reference does when CosmoParams holds ForwardDiff.Dual (examples/plot_deriv_cl.jl:28-33).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def need(name):
+    if not os.path.exists(os.path.join(GOLDEN, name)):
+        pytest.skip(f"{name} not generated (python tests/golden/make_golden.py <stage>)")
+    return load_golden(name)
+
+
+def device_cosmo_of(g, gpu_ctx):
+    from bolt_b200 import abi, capi
+    hc = abi.HostCosmo(g["scalars"], g["quad_pts"], g["quad_wts"], g["tables"], float(g["x0"]), float(g["dx"]))
+    return hc, capi.DeviceCosmo(gpu_ctx, hc)
+
+
+def rel_cl(got, ref, tt, ee, which):
+    """relative error of a spectrum; TE crosses zero, so it is measured against sqrt(TT EE)"""
+    den = np.sqrt(tt * ee) if which == "te" else np.abs(ref)
+    return np.abs(got - ref) / den
+
+
+def grad_err(got, ref, val_scale, pvals):
+    """north_star 'gradients within 1e-3 relative': |dC - dC_ref| / (|dC_ref| + 1e-2 |C| / |p|).  The floor only matters where
+    dlnC/dlnp < 1e-2, i.e. at sign changes of the derivative."""
+    return np.abs(got - ref) / (np.abs(ref) + 1e-2 * np.abs(val_scale)[:, None] / np.abs(pvals)[None, :])
+
+
+def test_c3_value_full_size_matches_oracle(gpu_ctx):
+    from bolt_b200 import abi
+    g = need("oracle_c3.npz")
+    hc, dc = device_cosmo_of(g, gpu_ctx)
+    H0 = hc.scalar("H0"); ix0 = int(g["ix_start"])
+    assert len(g["k"]) == 2000
+    o = abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6)
+    tt, te, ee, st, ns = dc.spectra(g["k"], o, g["ell"], 0.01 * H0, 1000 * H0, 5000, ix0)
+    assert np.all(st == 0) and np.all(g["status"] == 0)
+    assert rel_cl(tt, g["tt"], g["tt"], g["ee"], "tt").max() < 1e-4
+    assert rel_cl(ee, g["ee"], g["tt"], g["ee"], "ee").max() < 1e-4
+    assert rel_cl(te, g["te"], g["tt"], g["ee"], "te").max() < 1e-4
+    # same controller, same arithmetic up to rounding: the step sequences coincide for (nearly) every mode
+    same = (ns == g["nsteps"]).mean()
+    assert same > 0.9 and np.abs(ns - g["nsteps"]).max() <= 0.02 * g["nsteps"].max(), (same, np.abs(ns - g["nsteps"]).max())
+    assert np.array_equal(dc.last_nreject >= 0, np.ones(2000, bool))
+    # source columns of the stored sample of modes
+    sel = g["sel"]
+    out = dc.solve(g["k"][sel], abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6, ix_first=ix0), want=("S_T", "S_P"))
+    for key in ("S_T", "S_P"):
+        a, b = out[key][:, ix0:-1], g[key][:, :-1]
+        assert (np.abs(a - b).max(axis=1) / np.abs(b).max(axis=1)).max() < 1e-5, key
+
+
+def test_c4mini_lgamma50_matches_oracle(gpu_ctx):
+    from bolt_b200 import abi
+    g = need("oracle_c4mini.npz")
+    hc, dc = device_cosmo_of(g, gpu_ctx)
+    H0 = hc.scalar("H0"); ix0 = int(g["ix_start"])
+    o = abi.make_opts(50, 8, 10, reltol=1e-11, abstol=1e-6)
+    assert abi.state_dim(50, 8, 10, 15) == 281
+    tt, te, ee, st, ns = dc.spectra(g["k"], o, g["ell"], 0.01 * H0, 1000 * H0, 5000, ix0)
+    assert np.all(st == 0)
+    assert rel_cl(tt, g["tt"], g["tt"], g["ee"], "tt").max() < 1e-4
+    assert rel_cl(ee, g["ee"], g["tt"], g["ee"], "ee").max() < 1e-4
+    assert rel_cl(te, g["te"], g["tt"], g["ee"], "te").max() < 1e-4
+    out = dc.solve(g["k"][g["sel"]], abi.make_opts(50, 8, 10, reltol=1e-11, abstol=1e-6, ix_first=ix0), want=("S_T", "S_P"))
+    for key in ("S_T", "S_P"):
+        a, b = out[key][:, ix0:-1], g[key][:, :-1]
+        assert (np.abs(a - b).max(axis=1) / np.abs(b).max(axis=1)).max() < 1e-5, key
+
+
+def test_c2_plin_matches_oracle(gpu_ctx):
+    from bolt_b200 import abi, capi
+    g = need("oracle_c2.npz")
+    hc, dc = device_cosmo_of(g, gpu_ctx)         # tables with partials (nd = 7)
+    assert hc.nd == 7 and len(g["k"]) == 500
+    o = abi.make_opts(50, 50, 20, reltol=1e-5, abstol=1e-6)
+    # value-only run on the value tables
+    hv = abi.HostCosmo(g["scalars"][:, :1], g["quad_pts"], g["quad_wts"], g["tables"][:, :, :1], float(g["x0"]), float(g["dx"]))
+    dv = capi.DeviceCosmo(gpu_ctx, hv)
+    pk, st, ns = dv.plin(g["k"], o)
+    assert np.all(st == 0) and np.all(g["status"] == 0)
+    assert np.abs(pk / g["pk"] - 1).max() < 1e-4
+    # value + six partials on every 10th mode (generic kernel with partials, n = 473)
+    ks = g["k"][g["gsel"]]
+    pg, stg, nsg = dc.plin(ks, o)
+    ref = g["pk_grad"]
+    assert np.all(stg == 0) and pg.shape == ref.shape == (len(ks), 7)
+    assert np.abs(pg[:, 0] / ref[:, 0] - 1).max() < 1e-4
+    pvals = g["scalars"][[abi.S[nm] for nm in ("Ω_b", "Ω_c", "h", "n", "A", "Σm_ν")], 0]
+    assert grad_err(pg[:, 1:], ref[:, 1:], ref[:, 0], pvals).max() < 1e-3
+
+
+@pytest.fixture(scope="module")
+def c3grad(gpu_ctx):
+    g = need("oracle_c3grad_small.npz")
+    hc, dc = device_cosmo_of(g, gpu_ctx)
+    gpu_ctx.set_bessel_xmax(float(g["bessel_xmax"]))      # assume_nondual (spectra.jl:46-52): the table range carries no partials
+    yield g, hc, dc
+    gpu_ctx.set_bessel_xmax(0.0)
+
+
+def test_c3_gradients_nd7_sources_match_oracle(c3grad):
+    """K1 with partials as the bench runs it: six caller partials, four carried through the ODE (A and n never reach it)."""
+    from bolt_b200 import abi
+    g, hc, dc = c3grad
+    assert hc.nd == 7 and [str(s) for s in g["names"]] == ["Ω_b", "Ω_c", "h", "n", "A", "Σm_ν"]
+    ix0 = int(g["ix_start"]); sel = g["sel"]
+    o = abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6, ix_first=ix0)
+    out = dc.solve(g["k"][sel], o, want=("S_T", "S_P"))
+    assert np.all(out["status"] == 0) and out["S_T"].shape == (len(sel), hc.n_x, 7)
+    for key, last in (("S_T", -1), ("S_P", -21)):     # S_P ~ 1/y^2 is singular as x -> 0: compare below the last rows
+        a, b = out[key][:, ix0:last, :], g[key][:, :last, :]
+        sc = np.abs(b).max(axis=1, keepdims=True)      # per mode and component
+        nz = sc[:, 0, :] > 0
+        err = (np.abs(a - b) / np.where(sc > 0, sc, 1.0)).max(axis=1)
+        assert err[:, 0].max() < 1e-5, (key, err[:, 0].max())
+        assert err[:, 1:][nz[:, 1:]].max() < 1e-3, (key, err[:, 1:].max(axis=0))
+        assert np.all(a[:, :, [4, 5]] == 0) and np.all(b[:, :, [4, 5]] == 0)      # d/dn, d/dA: the hierarchy never sees them
+    # the error norm runs over value and partials (DiffEqBase semantics): ~3.5x the value-only step count, same on both sides
+    rel = np.abs(out["nsteps"] - g["nsteps"][sel]) / g["nsteps"][sel]
+    assert rel.max() < 0.02, rel
+
+
+def test_c3_gradients_nd7_spectra_match_oracle(c3grad):
+    """north_star: adaptive C_l (TT/TE/EE) within 1e-4 and ForwardDiff gradients within 1e-3 -- value and all six gradients
+    from ONE pass through K1 (NP = 4) and K2 (NP = 6)."""
+    from bolt_b200 import abi
+    g, hc, dc = c3grad
+    H0 = hc.scalar("H0"); ix0 = int(g["ix_start"])
+    o = abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6)
+    tt, te, ee, st, ns = dc.spectra(g["k"], o, g["ell"], 0.01 * H0, 1000 * H0, 5000, ix0)
+    assert np.all(st == 0) and tt.shape == g["tt"].shape == (len(g["ell"]), 7)
+    vtt, vee = g["tt"][:, 0], g["ee"][:, 0]
+    assert rel_cl(tt[:, 0], vtt, vtt, vee, "tt").max() < 1e-4
+    assert rel_cl(ee[:, 0], vee, vtt, vee, "ee").max() < 1e-4
+    assert rel_cl(te[:, 0], g["te"][:, 0], vtt, vee, "te").max() < 1e-4
+    pvals = g["scalars"][[abi.S[str(nm)] for nm in g["names"]], 0]
+    for got, ref, sc in ((tt, g["tt"], vtt), (ee, g["ee"], vee), (te, g["te"], np.sqrt(vtt * vee))):
+        e = grad_err(got[:, 1:], ref[:, 1:], sc, pvals)
+        assert e.max() < 1e-3, e.max(axis=0)
+    # exact structure: dC/dA = C/A
+    jA = 1 + [str(s) for s in g["names"]].index("A")
+    assert np.allclose(tt[:, jA] * pvals[jA - 1], tt[:, 0], rtol=1e-12)
