@@ -23,6 +23,11 @@
 
 using namespace bolt;
 
+namespace bolt {      // k1_cta.cu: the warp-specialised K1 (one CTA per k-mode), its own translation unit
+int k1_cta_init_constants();
+cudaError_t k1_cta_launch(const SolveParams& p, int num_sms, cudaStream_t st, int* grid_out);
+}
+
 struct PoolBlock { void* p; size_t bytes; bool used; };
 
 struct bolt_ctx {
@@ -125,6 +130,7 @@ int init_constants(bolt_ctx* ctx) {
   double rl1[MAX_L + 1];
   for (int l = 0; l <= MAX_L; l++) rl1[l] = 1.0 - rl[l];
   CUDA_OK(cudaMemcpyToSymbol(c_rl1, rl1, sizeof(rl1)));
+  if (k1_cta_init_constants()) return fail(ctx, BOLT_ERR_CUDA, "constant tables of k1_cta.cu");
   g_const_init[ctx->device] = true;
   return BOLT_OK;
 }
@@ -153,6 +159,16 @@ int launch_k1(bolt_ctx* ctx, const SolveParams& p) {
   CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
   kern<<<grid, 32, smem, ctx->stream>>>(p);
   CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->timing[4] += 1;
+  return BOLT_OK;
+}
+
+// One CTA per k-mode, warp-specialised (hierarchy_cta.cuh)
+int launch_k1_cta(bolt_ctx* ctx, const SolveParams& p) {
+  CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CUDA_OK(k1_cta_launch(p, ctx->num_sms, ctx->stream, nullptr));
   CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
   ctx->timing[4] += 1;
   return BOLT_OK;
@@ -234,6 +250,7 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   }
   const bool force_generic = getenv("BOLT_K1_GENERIC") != nullptr;     // development switch
   if (!force_generic && nq == 15 && p.Lnu == 8 && p.Lm == 10) {          // source_grid's truncations (src/spectra.jl:11)
+    if ((p.L == 8 || p.L == 10) && !getenv("BOLT_K1_WARP")) return launch_k1_cta(ctx, p);   // one CTA per mode; BOLT_K1_WARP=1: the one-warp kernel
     if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15, K1_NCH>>(ctx, p);         // l_gamma = 8: the reference default
     if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15, K1_NCH>>(ctx, p);       // l_gamma = 10: BASELINE config 1
   }

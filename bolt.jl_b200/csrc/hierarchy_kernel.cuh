@@ -51,13 +51,13 @@ struct SolveParams {
   int dbg_cap;
 };
 
-__constant__ double c_rl[MAX_L + 1];   // l/(2l+1)
-__constant__ double c_rl1[MAX_L + 1];  // 1 - l/(2l+1)
+static __constant__ double c_rl[MAX_L + 1];   // l/(2l+1)
+static __constant__ double c_rl1[MAX_L + 1];  // 1 - l/(2l+1)
 
 // KenCarp4 implicit tableau (Kennedy & Carpenter 2003, ARK4(3)6L[2]SA-ESDIRK); SURVEY 8c.
 #define KC_GAMMA 0.25
-__device__ __constant__ double KC_C[6] = {0.0, 0.5, 83.0 / 250.0, 31.0 / 50.0, 17.0 / 20.0, 1.0};
-__device__ __constant__ double KC_A[6][5] = {
+static __device__ __constant__ double KC_C[6] = {0.0, 0.5, 83.0 / 250.0, 31.0 / 50.0, 17.0 / 20.0, 1.0};
+static __device__ __constant__ double KC_A[6][5] = {
     {0, 0, 0, 0, 0},
     {1.0 / 4.0, 0, 0, 0, 0},
     {8611.0 / 62500.0, -1743.0 / 31250.0, 0, 0, 0},
@@ -65,7 +65,7 @@ __device__ __constant__ double KC_A[6][5] = {
     {15267082809.0 / 155376265600.0, -71443401.0 / 120774400.0, 730878875.0 / 902184768.0, 2285395.0 / 8070912.0, 0},
     {82889.0 / 524892.0, 0.0, 15625.0 / 83664.0, 69875.0 / 102672.0, -2260.0 / 8211.0}};
 // b - bhat (b = last row of A plus gamma)
-__device__ __constant__ double KC_E[6] = {
+static __device__ __constant__ double KC_E[6] = {
     82889.0 / 524892.0 - 4586570599.0 / 29645900160.0, 0.0,
     15625.0 / 83664.0 - 178811875.0 / 945068544.0, 69875.0 / 102672.0 - 814220225.0 / 1159782912.0,
     -2260.0 / 8211.0 + 3700637.0 / 11593932.0, 0.25 - 61727.0 / 225920.0};
@@ -698,8 +698,8 @@ __device__ __forceinline__ void ge4(const double (&Min)[4][4], const double (&rh
 template <bool CB> __device__ __forceinline__ double rl_of(int l) { return CB ? c_rl[l] : RLc(l); }
 template <bool CB> __device__ __forceinline__ double rl1_of(int l) { return CB ? c_rl1[l] : 1.0 - RLc(l); }
 
-template <class TR, bool CB = true>
-__device__ __forceinline__ void factor_reg(const Lane& ln, const BgS& b, double h, RegFactor<TR>& f) {
+template <class TR, bool CB = true, class FT>      // FT: RegFactor<TR> (lane-private scratch) or SlotFactor<TR> (hierarchy_cta.cuh)
+__device__ __forceinline__ void factor_reg(const Lane& ln, const BgS& b, double h, FT& f) {
   constexpr int MAXLEN = TR::MAXLEN;
   const int kind = ln.kind;
   const bool photon = (kind == CH_T || kind == CH_P);
@@ -1031,7 +1031,7 @@ __device__ __forceinline__ void rt_finish(const Lane& ln, const BgS& b, const Rt
 // MAXLEN > 0: interleaved layout [l][chain] (+5 scalars after MAXLEN*NCH) for the register-resident solver.
 template <class TR>
 __device__ __forceinline__ void lane_setup(const DevCosmo& c, const SolveParams& p, Lane& ln) {
-  ln.lane = threadIdx.x; ln.nq = c.nq; ln.L = p.L; ln.n = p.n;
+  ln.lane = threadIdx.x & 31; ln.nq = c.nq; ln.L = p.L; ln.n = p.n;
   ln.riS = 2 * (p.L + 1) + (p.Lnu + 1) + (p.Lm + 1) * c.nq;
   ln.maxlen = max(p.L, max(p.Lnu, p.Lm)) + 1;
   ln.q = 0; ln.df0 = 0; ln.wq = 0;
