@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 
 NK, ELL_MIN, ELL_MAX, LG, RELTOL, ABSTOL = 2000, 2, 2500, 8, 1e-11, 1e-6
 SEED = 20261017
+GRAD_NAMES = ["Ω_b", "Ω_c", "h", "n", "A", "Σm_ν"]
 
 
 def synthetic_params(i):
@@ -92,50 +93,95 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_sample(hcosmo, kstride=50, nell=25):
-    """The oracle port (all host cores) on a bounded sample of the step; returns extrapolated solves/s of a full step."""
+def host_threads():
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its children: the CPU arm overrides it
+    (oracle_set_num_threads), otherwise the OpenMP oracle would run single-threaded at N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample(hcosmo, kstride=50):
+    """One bounded sample of the step on the oracle port (all host cores): every kstride-th k-mode through the adaptive
+    solve and the SAME fraction of the multipoles through the projection.  Returns k-mode solves/s of the sample (the
+    sample's solves / its wall time: no extrapolation to the full step is involved) and the sample's wall time."""
     from bolt_b200 import abi
     from oracle.oracle import OracleCosmo, lib
+    lib().oracle_set_num_threads(host_threads())
     oc = OracleCosmo(hcosmo["hc"])
     cores = lib().oracle_num_threads()
     o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL, ix_first=hcosmo["ix_start"])
     ks = np.ascontiguousarray(hcosmo["k"][kstride // 2::kstride])
     t0 = time.perf_counter(); out = oc.solve(ks, o, want=("S_T", "S_P")); t_solve = time.perf_counter() - t0
-    ells = np.unique(np.linspace(ELL_MIN, ELL_MAX, nell).astype(np.int32))
+    nell_full = ELL_MAX - ELL_MIN + 1
+    ells = np.unique(np.linspace(ELL_MIN, ELL_MAX, max(2, round(nell_full * len(ks) / NK))).astype(np.int32))
     kmin, kmax, nkd = hcosmo["kd"]
     t0 = time.perf_counter(); oc.project(out["S_T"], out["S_P"], ks, ells, kmin, kmax, nkd, hcosmo["ix_start"]); t_proj = time.perf_counter() - t0
-    t_full = t_solve * (NK / len(ks)) + t_proj * ((ELL_MAX - ELL_MIN + 1) / len(ells))
-    return dict(value=NK / t_full, unit="k-mode solves/s", cores=cores, kind="port",
-                sample=f"every {kstride}th of the {NK} k-modes ({len(ks)} adaptive solves, {t_solve:.1f}s) + {len(ells)} of "
-                       f"{ELL_MAX - ELL_MIN + 1} multipoles ({t_proj:.1f}s), OpenMP over k and l, extrapolated linearly to the full step; "
-                       "C++ restatement with zero-skipping dense LU (faster than the reference's dense LU), not Julia"), t_solve + t_proj
+    t = t_solve + t_proj
+    return dict(value=len(ks) / t, unit="k-mode solves/s", cores=cores, kind="port",
+                sample=f"every {kstride}th of the {NK} k-modes ({len(ks)} adaptive solves, {t_solve:.1f}s) + the same fraction of the multipoles "
+                       f"({len(ells)} of {nell_full}, {t_proj:.1f}s), OpenMP over k and l on {cores} threads; value = sample solves / sample time; "
+                       "C++ restatement with zero-skipping dense LU (faster than the reference's dense LU), not Julia"), t
 
 
-def gradient_arm(ctx, ells):
-    """BASELINE configs[2] proper: the same C3 workload with forward-mode partials w.r.t. six parameters (value + gradient
-    from one pass, nd = 7).  tau is not a parameter of the reference: the sixth direction is the neutrino mass.
-    One warm-up and one timed step; reported beside the value-only headline, not instead of it."""
+def cpu_sample_gradients(dual, bg, kstride=125):
+    """The gradient workload (C3 with six forward-mode partials) on the oracle's dual-number stepper (generic dual arithmetic
+    on the restated right-hand side + dense LU, what the reference does with ForwardDiff.Dual parameters), bounded sample."""
+    from bolt_b200 import abi
+    from oracle.oracle import OracleCosmo, lib
+    import bolt_b200 as B
+    lib().oracle_set_num_threads(host_threads())
+    oc = OracleCosmo(dual)
+    cores = lib().oracle_num_threads()
+    k = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, NK)
+    ix0 = int(np.argmax(bg.x_grid > -8))
+    o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL, ix_first=ix0)
+    ks = np.ascontiguousarray(k[kstride // 2::kstride])
+    t0 = time.perf_counter(); out = oc.solve_sens(ks, o, want=("S_T", "S_P")); t_solve = time.perf_counter() - t0
+    nell_full = ELL_MAX - ELL_MIN + 1
+    ells = np.unique(np.linspace(ELL_MIN, ELL_MAX, max(2, round(nell_full * len(ks) / NK))).astype(np.int32))
+    t0 = time.perf_counter(); oc.project_sens(out["S_T"], out["S_P"], ks, ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, ix0); t_proj = time.perf_counter() - t0
+    t = t_solve + t_proj
+    return dict(value=len(ks) / t, unit="k-mode solves/s (value + 6 partials each)", cores=cores, kind="port",
+                sample=f"every {kstride}th of the {NK} k-modes ({len(ks)} dual-number solves, {t_solve:.1f}s) + the same fraction of the "
+                       f"multipoles ({len(ells)} of {nell_full}, {t_proj:.1f}s), {cores} threads; value = sample solves / sample time"), t
+
+
+def gradient_arm(ctx, ells, with_cpu=True):
+    """BASELINE configs[2] proper and the workload north_star's >= 100x target is quoted on: the C3 workload with forward-mode
+    partials w.r.t. six parameters (value + gradient from one pass, nd = 7).  tau is not a parameter of the reference:
+    the sixth direction is the neutrino mass.  One warm-up and three timed steps (host buffers: the e2e form), and the oracle's
+    dual-number stepper on a bounded sample of the same workload as its CPU baseline."""
     import bolt_b200 as B
     from bolt_b200 import abi, capi
     from bolt_b200.api import host_cosmo_with_partials
-    names = ["Ω_b", "Ω_c", "h", "n", "A", "Σm_ν"]
     par = synthetic_params(0)
-    dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, names, rel_step=1e-3)
+    dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, GRAD_NAMES, rel_step=1e-3)
     dc = capi.DeviceCosmo(ctx, dual)
     k = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, NK)
     o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL)
     ix0 = int(np.argmax(bg.x_grid > -8))
-    out = None
-    for rep in range(2):
-        t0 = time.perf_counter()
+    out = dc.spectra(k, o, ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, ix0)
+    nrep = 3
+    t0 = time.perf_counter()
+    for rep in range(nrep):
         out = dc.spectra(k, o, ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, ix0)
-        dt = time.perf_counter() - t0
+    dt = (time.perf_counter() - t0) / nrep
     tm = ctx.timing()
-    return {"params": names, "nd": 7, "ms_per_step": 1e3 * dt, "spectra_with_gradients_per_s": 1.0 / dt, "kmode_solves_per_s": NK / dt,
-            "kernel_ms": {"hierarchy": tm["hierarchy_ms"], "bessel_tables": tm["bessel_ms"], "projection": tm["project_ms"]},
-            "ode_steps_per_solve": float(out[4].mean()), "failed_modes": int((out[3] != 0).sum()),
-            "note": "host tables' partials by central differences of the Python host generator (the Julia shim passes ForwardDiff "
-                    "partials); error control runs over value and partials like the reference, hence more steps than value-only"}
+    res = {"workload": "C3 with gradients: the C3 workload with 6 forward-mode partials (nd = 7), TT+TE+EE and their gradients",
+           "params": GRAD_NAMES, "nd": 7, "ms_per_step": 1e3 * dt, "spectra_with_gradients_per_s": 1.0 / dt, "value": NK / dt,
+           "unit": "k-mode solves/s (value + 6 partials each)", "timed_steps": nrep,
+           "kernel_ms": {"hierarchy": tm["hierarchy_ms"], "bessel_tables": tm["bessel_ms"], "projection": tm["project_ms"]},
+           "ode_steps_per_solve": float(out[4].mean()), "failed_modes": int((out[3] != 0).sum()),
+           "note": "host tables' partials by central differences of the Python host generator (the Julia shim passes ForwardDiff "
+                   "partials); error control runs over value and partials like the reference, hence more steps than value-only"}
+    if with_cpu:
+        cb, _ = cpu_sample_gradients(dual, bg)
+        res["cpu_baseline"] = cb
+        res["speedup_vs_cpu_baseline"] = res["value"] / cb["value"]
+        res["north_star_target"] = ">= 100x the all-core CPU spectra/s for TT+EE with gradients at 1 B200"
+    return res
 
 
 def plin_arm(ctx, hcosmo, dc):
@@ -188,22 +234,23 @@ def main():
                     "source grids 64 MB) > 126 MB L2, and alternates between two cosmologies"}
 
     if args.impl == "reference":
+        # Rank 0 alone runs the CPU arm (with every host core, whatever OMP_NUM_THREADS torchrun exported); other ranks exit 0.
         if rank != 0:
             return
         hcos = make_host_cosmo(0)
-        vals = []
-        for i in range(args.warmup + args.steps):
-            cb, _ = cpu_sample(hcos)
+        vals, secs = [], []
+        for i in range(args.warmup + args.steps):       # every step = one bounded sample (cpu_sample docstring), ~2-3 s each
+            cb, t = cpu_sample(hcos)
             if i >= args.warmup:
-                vals.append(cb["value"])
-            if i == 0 and args.warmup > 1:      # the CPU path has no warm-up effects worth minutes of host time
-                args.warmup = 1
-        v = float(np.mean(vals))
+                vals.append(cb["value"]); secs.append(t)
+        v = float(len(vals) * len(hcos["k"][25::50]) / np.sum(secs))          # sample solves of the timed steps / their time
         cb["value"] = v
         print(json.dumps({"impl": "reference", "metric": "kmode_hierarchy_solves_per_s", "value": v, "unit": "k-mode solves/s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * NK / v,
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": config, "cpu_baseline": cb,
+                          "step_note": "a step of this arm is a bounded sample of the workload (1/50 of the k-modes and of the multipoles); "
+                                       "value = sample k-mode solves / sample time, so ms_per_step is the sample's time, not a full spectrum set",
                           "e2e": {"value": v, "unit": "k-mode solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -237,7 +284,7 @@ def main():
         o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL)
         kmin, kmax, nkd = h["kd"]
         tt, te, ee, st, ns = dc.spectra(h["k"], o, ells, kmin, kmax, nkd, h["ix_start"])
-        return tt, te, ee, st, ns, ctx.timing()
+        return tt, te, ee, st, ns + dc.last_nreject, ctx.timing()
 
     def step_e2e(i):
         h = hcos[(i + phase) % 2]
@@ -281,15 +328,13 @@ def main():
     if rank == 0:
         total_solves = NK * args.steps * world
         value = total_solves / wall_max
-        # rejected steps cost the same as accepted ones; nreject is not returned by bolt_spectra: use the oracle-verified
-        # ratio from the accepted count only (lower bound on work)
-        fl = nstep_tot * f_step(n)
+        fl = nstep_tot * f_step(n)        # accepted + rejected step attempts (bolt_spectra returns both counts)
         roof = {"kernel": "hierarchy_kernel (K1, dominant)", "bound": "fp64", "achieved": fl / (k1_ms * 1e-3) / 1e12, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": fl / (k1_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                "traffic": 1.16e6, "traffic_note": "dram bytes read+write per launch from profiles/r1_k1_hierarchy.md (ncu --set full): K1 is not HBM bound",
+                "traffic": None, "traffic_note": "not measured in this run; ncu --set full of this kernel (profiles/, see profiles/README.md for the capture's commit): "
+                                                 "~1 MB of DRAM traffic per launch -- K1 is not HBM bound",
                 "peak_source": "DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
-                "note": "algorithmic flop = accepted steps x (182 n + 3300), n = 197 (DESIGN.md); ncu: FP64 pipe active 26% of cycles, "
-                        "issue slots 36% -- issue- and instruction-fetch bound at 8 warps/SM (profiles/r1_k1_hierarchy_v6.md)"}
+                "note": "algorithmic flop = step attempts (accepted + rejected) x (182 n + 3300), n = 197 (DESIGN.md); stall analysis in profiles/"}
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -299,7 +344,7 @@ def main():
         k2_bytes = (2 * 799 * 4999 * 8) + nell * 5003 * 8      # one read of the dense source grids + the spline tables
         k2_terms = 2.0 * nell * 4999 * 799
         roof_k2 = {"kernel": "project_kernel (K2)", "bound": "hbm", "achieved": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                   "unit": "GB/s", "frac": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": 2.99e8,
+                   "unit": "GB/s", "frac": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                    "fp64_tflops": 25.0 * k2_terms / 2 * args.steps / (k2_ms * 1e-3) / 1e12,
                    "note": "K2 is FP64/shared-memory-gather bound, not HBM bound (SURVEY 8d): both figures reported"}
         line = {"metric": "kmode_hierarchy_solves_per_s", "value": value, "unit": "k-mode solves/s", "n_gpus": world, "steps": args.steps,
@@ -309,7 +354,7 @@ def main():
                 "kernel_ms_per_step": {"hierarchy": k1_ms / args.steps, "bessel_tables": bes_ms / args.steps, "projection": k2_ms / args.steps},
                 "kernel_ms_note": "bessel_tables is the elapsed time of the second stream, enqueued behind K1's launch to fill its tail: it is "
                                   "mostly waiting for SMs (the two table kernels take 3.7 + 3.0 ms alone) and overlaps hierarchy",
-                "ode_steps_per_solve": nstep_tot / (NK * args.steps), "failed_modes": bad,
+                "ode_step_attempts_per_solve": nstep_tot / (NK * args.steps), "failed_modes": bad,
                 "roofline": roof, "roofline_k2": roof_k2, "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": total_solves / e2e_max, "unit": "k-mode solves/s",
                         "h2d_bytes_per_step": int(hcos[0]["hc"].tables.nbytes + hcos[0]["hc"].scalars.nbytes + 2 * 15 * 8 + NK * 8 + nell * 4 + 2 * NK * 4),
@@ -324,7 +369,7 @@ def main():
             except Exception as e:          # noqa: BLE001 -- reported in the JSON line instead of aborting the benchmark
                 return {"error": f"{type(e).__name__}: {e}"[:300]}
         if not args.no_gradients and world == 1:
-            line["gradients"] = guarded(gradient_arm, ctx, ells)
+            line["gradients"] = guarded(gradient_arm, ctx, ells, not args.no_cpu_baseline)
         if world == 1:
             line["plin"] = guarded(plin_arm, ctx, hcos[0], dcs[0])
             line["batch"] = guarded(batch_arm, ctx, hcos, dcs, ells)

@@ -250,7 +250,10 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   }
   const bool force_generic = getenv("BOLT_K1_GENERIC") != nullptr;     // development switch
   if (!force_generic && nq == 15 && p.Lnu == 8 && p.Lm == 10) {          // source_grid's truncations (src/spectra.jl:11)
-    if ((p.L == 8 || p.L == 10) && !getenv("BOLT_K1_WARP")) return launch_k1_cta(ctx, p);   // one CTA per mode; BOLT_K1_WARP=1: the one-warp kernel
+    // one CTA per mode (lower per-mode latency) while every mode finds a resident CTA; beyond that the one-warp kernel has the
+    // higher throughput (measured: 296 modes 27.5 vs 33.5 ms, 2000 modes 59.7 vs 48.2 ms).  BOLT_K1_WARP=1 / BOLT_K1_CTA=1 force one.
+    const bool want_cta = getenv("BOLT_K1_CTA") || (!getenv("BOLT_K1_WARP") && p.nk <= 4 * ctx->num_sms);
+    if ((p.L == 8 || p.L == 10) && want_cta) return launch_k1_cta(ctx, p);
     if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15, K1_NCH>>(ctx, p);         // l_gamma = 8: the reference default
     if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15, K1_NCH>>(ctx, p);       // l_gamma = 10: BASELINE config 1
   }
