@@ -26,6 +26,8 @@ using namespace bolt;
 namespace bolt {      // k1_cta.cu: the warp-specialised K1 (one CTA per k-mode), its own translation unit
 int k1_cta_init_constants();
 cudaError_t k1_cta_launch(const SolveParams& p, int num_sms, cudaStream_t st, int* grid_out);
+int k1_pipe_init_constants();      // k1_pipe.cu: the pipelined K1 (one CTA per k-mode, six warps by role)
+cudaError_t k1_pipe_launch(const SolveParams& p, int num_sms, cudaStream_t st, int* grid_out);
 }
 
 struct PoolBlock { void* p; size_t bytes; bool used; };
@@ -131,6 +133,7 @@ int init_constants(bolt_ctx* ctx) {
   for (int l = 0; l <= MAX_L; l++) rl1[l] = 1.0 - rl[l];
   CUDA_OK(cudaMemcpyToSymbol(c_rl1, rl1, sizeof(rl1)));
   if (k1_cta_init_constants()) return fail(ctx, BOLT_ERR_CUDA, "constant tables of k1_cta.cu");
+  if (k1_pipe_init_constants()) return fail(ctx, BOLT_ERR_CUDA, "constant tables of k1_pipe.cu");
   g_const_init[ctx->device] = true;
   return BOLT_OK;
 }
@@ -169,6 +172,16 @@ int launch_k1_cta(bolt_ctx* ctx, const SolveParams& p) {
   CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
   CUDA_OK(k1_cta_launch(p, ctx->num_sms, ctx->stream, nullptr));
+  CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->timing[4] += 1;
+  return BOLT_OK;
+}
+
+// One CTA per k-mode, six warps by role (hierarchy_pipe.cuh)
+int launch_k1_pipe(bolt_ctx* ctx, const SolveParams& p) {
+  CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, 257 * sizeof(int), ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CUDA_OK(k1_pipe_launch(p, ctx->num_sms, ctx->stream, nullptr));
   CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
   ctx->timing[4] += 1;
   return BOLT_OK;
@@ -250,10 +263,14 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   }
   const bool force_generic = getenv("BOLT_K1_GENERIC") != nullptr;     // development switch
   if (!force_generic && nq == 15 && p.Lnu == 8 && p.Lm == 10) {          // source_grid's truncations (src/spectra.jl:11)
-    // one CTA per mode (lower per-mode latency) while every mode finds a resident CTA; beyond that the one-warp kernel has the
-    // higher throughput (measured: 296 modes 27.5 vs 33.5 ms, 2000 modes 59.7 vs 48.2 ms).  BOLT_K1_WARP=1 / BOLT_K1_CTA=1 force one.
-    const bool want_cta = getenv("BOLT_K1_CTA") || (!getenv("BOLT_K1_WARP") && p.nk <= 4 * ctx->num_sms);
-    if ((p.L == 8 || p.L == 10) && want_cta) return launch_k1_cta(ctx, p);
+    // Two kernels for source_grid's truncations.  The pipelined CTA-per-mode kernel (hierarchy_pipe.cuh) has 2.1-2.6x lower
+    // per-mode latency (one mode: 12.9 vs 33.1 ms; 296 modes: 15.4 vs 33.1 ms) but holds only 2 modes per SM; the one-warp-per-mode
+    // kernel holds 8 and wins once the modes outnumber the resident CTAs several times (2000 modes: 59.6 vs 46.8 ms).
+    // BOLT_K1_PIPE=1 / BOLT_K1_WARP=1 / BOLT_K1_CTA=1 (the first CTA kernel, kept for comparison) force one.
+    if (p.L == 8 || p.L == 10) {
+      if (getenv("BOLT_K1_CTA")) return launch_k1_cta(ctx, p);
+      if (getenv("BOLT_K1_PIPE") || (!getenv("BOLT_K1_WARP") && p.nk <= 4 * ctx->num_sms)) return launch_k1_pipe(ctx, p);
+    }
     if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15, K1_NCH>>(ctx, p);         // l_gamma = 8: the reference default
     if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15, K1_NCH>>(ctx, p);       // l_gamma = 10: BASELINE config 1
   }
@@ -479,7 +496,8 @@ int bolt_init(int device_ordinal, bolt_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
   if (cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
   for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return BOLT_ERR_CUDA; }
-  if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return BOLT_ERR_ALLOC; }
+  // work-queue head + per-SM resident-CTA counters (k1_pipe)
+  if (cudaMalloc(&ctx->d_counter, 257 * sizeof(int)) != cudaSuccess) { delete ctx; return BOLT_ERR_ALLOC; }
   if (init_constants(ctx) != BOLT_OK) { delete ctx; return BOLT_ERR_CUDA; }
   if (getenv("BOLT_DEBUG_STEPS")) { cudaMalloc(&ctx->d_dbg, sizeof(double) * 4 * DBG_CAP); cudaMemset(ctx->d_dbg, 0, sizeof(double) * 4 * DBG_CAP); }
   *out = ctx;

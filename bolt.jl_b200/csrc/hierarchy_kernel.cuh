@@ -629,6 +629,8 @@ struct BgS {
   double H, eta, taup, csb2, a;
   double kappa, qe, eq, wPsi, wPhi, cPsi, gPhi, k2, R, Oc_a, Ob_a, iHeta;
 };
+// ... from the four table values H, eta, tau', c_sb^2 at x (already in b)
+__device__ __forceinline__ void bg_from_tables(const Lane& ln, const ModeConst& mc, double x, BgS& b);
 __device__ __forceinline__ void eval_bg_fast(const DevCosmo& c, const Lane& ln, const ModeConst& mc, double x, BgS& b) {
   // every lane evaluates one of the four tables (lane & 3): no divergent branch, the extra loads are broadcasts
   static_assert(BOLT_T_H == 0 && BOLT_T_eta == 3 && BOLT_T_taup == 6 && BOLT_T_csb2 == 11, "table order");
@@ -636,6 +638,9 @@ __device__ __forceinline__ void eval_bg_fast(const DevCosmo& c, const Lane& ln, 
   const int tab = 3 * wl + ((wl == 3) ? 2 : 0);       // = which[wl] without a select chain
   const double v = spline_eval(c.tab[tab], c.n_x, c.x0, c.dx, x);
   b.H = shfl_d(v, 0); b.eta = shfl_d(v, 1); b.taup = shfl_d(v, 2); b.csb2 = shfl_d(v, 3);
+  bg_from_tables(ln, mc, x, b);
+}
+__device__ __forceinline__ void bg_from_tables(const Lane& ln, const ModeConst& mc, double x, BgS& b) {
   b.a = exp(x);
   const double ia = fast_rcp(b.a), ia2 = ia * ia, iH = fast_rcp(b.H), iH2 = iH * iH;
   b.kappa = mc.k * iH; b.R = mc.R0 * ia; b.cPsi = mc.c12 * ia2; b.gPhi = mc.H02h * iH2; b.k2 = mc.k2_3 * iH2;
@@ -1030,8 +1035,8 @@ __device__ __forceinline__ void rt_finish(const Lane& ln, const BgS& b, const Rt
 // Chain ownership of a lane for cosmology c.  MAXLEN == 0: generic layout = the reference's unpack order.
 // MAXLEN > 0: interleaved layout [l][chain] (+5 scalars after MAXLEN*NCH) for the register-resident solver.
 template <class TR>
-__device__ __forceinline__ void lane_setup(const DevCosmo& c, const SolveParams& p, Lane& ln) {
-  ln.lane = threadIdx.x & 31; ln.nq = c.nq; ln.L = p.L; ln.n = p.n;
+__device__ __forceinline__ void lane_setup(const DevCosmo& c, const SolveParams& p, Lane& ln, int lane = threadIdx.x & 31) {
+  ln.lane = lane; ln.nq = c.nq; ln.L = p.L; ln.n = p.n;
   ln.riS = 2 * (p.L + 1) + (p.Lnu + 1) + (p.Lm + 1) * c.nq;
   ln.maxlen = max(p.L, max(p.Lnu, p.Lm)) + 1;
   ln.q = 0; ln.df0 = 0; ln.wq = 0;
