@@ -2,7 +2,7 @@
 import ctypes as C
 import numpy as np
 
-BOLT_ABI_VERSION = 2
+BOLT_ABI_VERSION = 3
 
 SCALARS = ["h", "Ω_r", "Ω_b", "Ω_c", "A", "n", "Y_p", "N_ν", "Σm_ν", "H0", "η0", "ρ_crit", "Ω_Λ"]
 TABLES = ["H", "Hp", "Hpp", "η", "ρ0M", "τ", "τp", "τpp", "g", "gp", "gpp", "csb2"]

@@ -15,7 +15,8 @@ _LIB = None
 
 EXPORTS = ["bolt_abi_version", "bolt_init", "bolt_finalize", "bolt_last_error", "bolt_last_timing",
            "bolt_cosmo_upload", "bolt_cosmo_free", "bolt_state_dim", "bolt_solve", "bolt_project",
-           "bolt_spectra", "bolt_spectra_batch", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak", "bolt_set_bessel_xmax"]
+           "bolt_spectra", "bolt_spectra_batch", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak", "bolt_set_bessel_xmax",
+           "bolt_comm_unique_id", "bolt_comm_init", "bolt_comm_free", "bolt_spectra_sharded", "bolt_shard_plan"]
 
 
 class BoltError(RuntimeError):
@@ -50,6 +51,11 @@ def lib():
         L.bolt_set_bessel_xmax.argtypes = [vp, C.c_double]
         L.bolt_solve_device.argtypes = [vp, vp, vp, C.c_int, C.POINTER(abi.Opts), vp, vp, vp, vp, vp, vp]
         L.bolt_project_device.argtypes = [vp, vp, vp, vp, vp, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, vp]
+        L.bolt_comm_unique_id.argtypes = [vp, vp]
+        L.bolt_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.bolt_comm_free.argtypes = [vp]
+        L.bolt_spectra_sharded.argtypes = L.bolt_spectra.argtypes
+        L.bolt_shard_plan.argtypes = [dp, C.c_int, C.c_int, C.c_int, ip, ip]
         _LIB = L
     return _LIB
 
@@ -82,6 +88,29 @@ class Context:
         t = np.zeros(1)
         self.check(lib().bolt_fp64_peak(self._h, abi.ptr(t)))
         return float(t[0])
+
+    # ---- multi-GPU: one context per rank; the host only carries the 128-byte id from rank 0 to the others -------------
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        self.check(lib().bolt_comm_unique_id(self._h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def comm_init(self, rank, nranks, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self.check(lib().bolt_comm_init(self._h, int(rank), int(nranks), C.cast(buf, C.c_void_p)))
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    def comm_init_torch(self, group=None):
+        """Bootstrap the library's communicator from an initialised torch.distributed process group (any backend)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        self.comm_init(rank, world, box[0])
+
+    def comm_free(self):
+        if self._h:
+            lib().bolt_comm_free(self._h)
 
     def close(self):
         if self._h:
@@ -178,6 +207,20 @@ class DeviceCosmo:
         self.last_nreject = nr          # rejected steps per mode of the last call (cost as much as accepted ones)
         return tt, te, ee, st, ns
 
+    def spectra_sharded(self, k, opts, ells, kd_min, kd_max, n_kd, ix_start):
+        """bolt_spectra_sharded: collective over the ranks of the context's communicator (Context.comm_init)."""
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        ells = np.ascontiguousarray(ells, dtype=np.int32)
+        shp = (len(ells),) if self.hc.nd == 1 else (len(ells), self.hc.nd)
+        tt, te, ee = np.zeros(shp), np.zeros(shp), np.zeros(shp)
+        st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64); nr = np.zeros(len(k), dtype=np.int64)
+        self.ctx.check(lib().bolt_spectra_sharded(self.ctx._h, self._h, abi.ptr(k), len(k), C.byref(opts),
+                                                  abi.ptr(ells, abi.c_int32_p), len(ells), kd_min, kd_max, n_kd, ix_start,
+                                                  abi.ptr(tt), abi.ptr(te), abi.ptr(ee), abi.ptr(st, abi.c_int32_p),
+                                                  abi.ptr(ns, abi.c_int64_p), abi.ptr(nr, abi.c_int64_p)))
+        self.last_nreject = nr
+        return tt, te, ee, st, ns
+
     def plin(self, k, opts):
         k = np.ascontiguousarray(k, dtype=np.float64)
         pk = np.zeros(len(k) if self.hc.nd == 1 else (len(k), self.hc.nd))
@@ -214,3 +257,13 @@ class DeviceCosmo:
         self.ctx.check(lib().bolt_project_device(self.ctx._h, self._h, S_T.data_ptr(), S_P.data_ptr(), k_t.data_ptr(), k_t.numel(),
                                                  abi.ptr(ells, abi.c_int32_p), len(ells), kd_min, kd_max, n_kd, ix_start, cl.data_ptr()))
         return cl
+
+
+def shard_plan(k, rank, nranks):
+    """bolt_shard_plan (host only): indices into k that `rank` of `nranks` solves, in work order (descending k, cyclic)."""
+    k = np.ascontiguousarray(k, dtype=np.float64)
+    idx = np.zeros(len(k), dtype=np.int32); n = np.zeros(1, dtype=np.int32)
+    rc = lib().bolt_shard_plan(abi.ptr(k), len(k), int(rank), int(nranks), abi.ptr(idx, abi.c_int32_p), abi.ptr(n, abi.c_int32_p))
+    if rc != 0:
+        raise BoltError(f"bolt_shard_plan failed with {rc}")
+    return idx[:int(n[0])].copy()

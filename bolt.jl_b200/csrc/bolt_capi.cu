@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <memory>
+#include <dlfcn.h>
 
 // shared-memory layout of the register-resident value kernel: 19 = nq + 4 (compact + shared all-zero column for the idle
 // lanes, flat stage assembly: 3 % faster), 32 = one private column per lane
@@ -45,6 +46,8 @@ struct bolt_ctx {
   int* d_counter = nullptr;
   double bessel_xmax = 0.0;  // 0: kgrid[end]*eta0 (src/spectra.jl:85); > 0: caller-fixed table range (bolt_set_bessel_xmax)
   double* d_dbg = nullptr;   // step log (only when BOLT_DEBUG_STEPS is set)
+  void* comm = nullptr;      // ncclComm_t of this rank (bolt_comm_init); collectives run on `stream`
+  int rank = 0, nranks = 1;
 };
 constexpr int DBG_CAP = 1 << 16;
 
@@ -78,6 +81,21 @@ __global__ void eta_end_kernel(DevCosmo* c) {
 }
 
 namespace {
+
+// NCCL entry points, bound at run time (bolt_comm_*): see the multi-GPU section below
+struct NcclId128 { char b[128]; };          // ncclUniqueId (nccl.h: 128 opaque bytes, passed by value)
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+constexpr int NCCL_INT32 = 2, NCCL_INT64 = 4, NCCL_FLOAT64 = 8, NCCL_SUM = 0;      // ncclDataType_t / ncclRedOp_t (nccl.h, stable ABI)
 
 int fail(bolt_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
@@ -269,7 +287,7 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
     // BOLT_K1_PIPE=1 / BOLT_K1_WARP=1 / BOLT_K1_CTA=1 (the first CTA kernel, kept for comparison) force one.
     if (p.L == 8 || p.L == 10) {
       if (getenv("BOLT_K1_CTA")) return launch_k1_cta(ctx, p);
-      if (getenv("BOLT_K1_PIPE") || (!getenv("BOLT_K1_WARP") && p.nk <= 4 * ctx->num_sms)) return launch_k1_pipe(ctx, p);
+      if (getenv("BOLT_K1_PIPE") || (!getenv("BOLT_K1_WARP") && p.nk <= 8 * ctx->num_sms)) return launch_k1_pipe(ctx, p);
     }
     if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15, K1_NCH>>(ctx, p);         // l_gamma = 8: the reference default
     if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15, K1_NCH>>(ctx, p);       // l_gamma = 10: BASELINE config 1
@@ -508,6 +526,7 @@ int bolt_finalize(bolt_ctx* ctx) {
   if (!ctx) return BOLT_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
   for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& b : ctx->pool) cudaFree(b.p);
   cudaFree(ctx->d_counter);
@@ -903,6 +922,182 @@ int bolt_project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_S_T,
   if (rc) return rc;
   CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return collect_timing(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-GPU: the k-modes of ONE cosmology sharded over the ranks of a communicator (the reference's fan-out over
+// k is the threaded map of src/spectra.jl:10, its fan-out over l the qmap of :149).  One process per GPU, one context per
+// process; the host (MPI.jl / torch.distributed / a file) only carries the 128-byte unique id from rank 0 to the others.
+// NCCL is bound at run time (dlopen) so that single-GPU users do not need it; a process that already loaded an NCCL (e.g.
+// torch's) shares that copy.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+int nccl_load(bolt_ctx* ctx) {
+  std::lock_guard<std::mutex> lock(g_nccl_mutex);
+  if (g_nccl.lib) return BOLT_OK;
+  const char* names[] = {getenv("BOLT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* nm : names) if (nm && (h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!h) return fail(ctx, BOLT_ERR_UNSUPPORTED, "NCCL not found (libnccl.so.2); set BOLT_NCCL_LIB");
+#define BOLT_NCCL_SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) return fail(ctx, BOLT_ERR_UNSUPPORTED, "NCCL symbol missing: " name);
+  BOLT_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") BOLT_NCCL_SYM(CommInitRank, "ncclCommInitRank") BOLT_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  BOLT_NCCL_SYM(AllGather, "ncclAllGather") BOLT_NCCL_SYM(AllReduce, "ncclAllReduce") BOLT_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef BOLT_NCCL_SYM
+  g_nccl.lib = h;
+  return BOLT_OK;
+}
+int nccl_fail(bolt_ctx* ctx, int rc, const char* what) {
+  return fail(ctx, BOLT_ERR_CUDA, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error"));
+}
+#define NCCL_OK(call, what) do { int rc_ = (call); if (rc_ != 0) return nccl_fail(ctx, rc_, what); } while (0)
+
+// gathered [R][2][per][row] -> S_T, S_P [nk][row] in the caller's k order: shard r, slot j holds mode order[r + j*R]
+__global__ void unshard_sources_kernel(const double* __restrict__ g, const int* __restrict__ order, int nk, int R, int per, int row,
+                                       double* __restrict__ S_T, double* __restrict__ S_P) {
+  const int pos = blockIdx.x;                 // position in the descending-k order
+  const int r = pos % R, j = pos / R;
+  const int ik = order[pos];
+  const double* src = g + ((size_t)r * 2 * per + j) * row;
+  for (int i = threadIdx.x; i < row; i += blockDim.x) {
+    S_T[(size_t)ik * row + i] = src[i];
+    S_P[(size_t)ik * row + i] = src[(size_t)per * row + i];
+  }
+}
+// local [3][nl][nd] (multipoles rank, rank+R, ...) -> full [3][nell][nd], zero elsewhere (the all-reduce then concatenates)
+__global__ void scatter_cl_kernel(const double* __restrict__ loc, int nl, int nell, int nd, int rank, int R, double* __restrict__ full) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * nl * nd) return;
+  const int d = i % nd, il = (i / nd) % nl, s = i / (nd * nl);
+  full[((size_t)s * nell + (rank + (size_t)il * R)) * nd + d] = loc[i];
+}
+}  // namespace
+
+int bolt_shard_plan(const double* k, int nk, int rank, int nranks, int32_t* idx, int32_t* n_local) {
+  if (!k || nk < 1 || nranks < 1 || rank < 0 || rank >= nranks || !idx || !n_local) return BOLT_ERR_ARG;
+  std::vector<int> order(nk);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return k[a] > k[b]; });
+  int n = 0;
+  for (int pos = rank; pos < nk; pos += nranks) idx[n++] = order[pos];
+  *n_local = n;
+  return BOLT_OK;
+}
+
+int bolt_comm_unique_id(bolt_ctx* ctx, void* id128) {
+  if (!ctx || !id128) return BOLT_ERR_ARG;
+  int rc = nccl_load(ctx); if (rc) return rc;
+  NCCL_OK(g_nccl.GetUniqueId(id128), "ncclGetUniqueId");
+  return BOLT_OK;
+}
+
+int bolt_comm_init(bolt_ctx* ctx, int rank, int nranks, const void* id128) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return ctx ? fail(ctx, BOLT_ERR_ARG, "bad communicator arguments") : BOLT_ERR_ARG;
+  if (ctx->comm) return fail(ctx, BOLT_ERR_ARG, "communicator already initialised");
+  int rc = nccl_load(ctx); if (rc) return rc;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  NcclId128 id; memcpy(id.b, id128, 128);
+  NCCL_OK(g_nccl.CommInitRank(&ctx->comm, nranks, id, rank), "ncclCommInitRank");
+  ctx->rank = rank; ctx->nranks = nranks;
+  return BOLT_OK;
+}
+
+int bolt_comm_free(bolt_ctx* ctx) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (ctx->comm) { cudaStreamSynchronize(ctx->stream); g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; ctx->rank = 0; ctx->nranks = 1; }
+  return BOLT_OK;
+}
+
+// bolt_spectra with the k-modes (K1) and the multipoles (K2) sharded over the communicator's ranks.  Every rank passes the
+// SAME arguments and receives the SAME complete results.  K1 on the rank's cyclic shard of the descending-k order -> one
+// ncclAllGather of the source columns (C_l is quadratic in the k-interpolated source, src/spectra.jl:91-93: both bracketing
+// coarse columns must be present everywhere) -> K2 on multipoles rank, rank+R, ... -> ONE ncclAllReduce(sum) of the C_l vector
+// (disjoint supports) -- all on the context's stream.  Without a communicator (or with one rank) it is bolt_spectra.
+int bolt_spectra_sharded(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
+                         const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start,
+                         double* cl_tt, double* cl_te, double* cl_ee, int32_t* status, int64_t* nsteps, int64_t* nreject) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (!ctx->comm || ctx->nranks == 1)
+    return bolt_spectra(ctx, c, k, nk, o, ell, nell, kd_min, kd_max, n_kd, ix_start, cl_tt, cl_te, cl_ee, status, nsteps, nreject);
+  if (!c || !k || nk < 2 || !ell || nell < 1) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
+  int rc = check_opts(ctx, c, o); if (rc) return rc;
+  rc = check_projection_args(ctx, c, ell, nell, n_kd, ix_start); if (rc) return rc;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  reset_timing(ctx);
+  CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const int R = ctx->nranks, rank = ctx->rank;
+  const int nd = c->h.nd, row = c->h.n_x * nd;
+  const int per = (nk + R - 1) / R;
+  // descending-k order; this rank's shard = positions rank, rank+R, ...
+  std::vector<int> order(nk);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return k[a] > k[b]; });
+  std::vector<double> kloc; std::vector<int> ident;
+  for (int pos = rank; pos < nk; pos += R) { kloc.push_back(k[order[pos]]); ident.push_back((int)ident.size()); }
+  const int nloc = (int)kloc.size();
+  DevBuf<double> d_k, d_kloc, d_loc, d_gath, d_ST, d_SP, d_cl_loc, d_cl; DevBuf<int> d_order, d_ident, d_st_loc, d_st_all;
+  DevBuf<long long> d_cnt_loc, d_cnt_all;
+  CUDA_OK(d_k.alloc(ctx, nk)); CUDA_OK(d_order.alloc(ctx, nk)); CUDA_OK(d_kloc.alloc(ctx, std::max(nloc, 1))); CUDA_OK(d_ident.alloc(ctx, std::max(nloc, 1)));
+  CUDA_OK(cudaMemcpyAsync(d_k.p, k, nk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(d_order.p, order.data(), nk * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (nloc) {
+    CUDA_OK(cudaMemcpyAsync(d_kloc.p, kloc.data(), nloc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(d_ident.p, ident.data(), nloc * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));     // host vectors are locals
+  CUDA_OK(d_loc.alloc(ctx, (size_t)2 * per * row)); CUDA_OK(d_gath.alloc(ctx, (size_t)R * 2 * per * row));
+  CUDA_OK(d_ST.alloc(ctx, (size_t)nk * row)); CUDA_OK(d_SP.alloc(ctx, (size_t)nk * row));
+  CUDA_OK(d_st_loc.alloc(ctx, per)); CUDA_OK(d_st_all.alloc(ctx, (size_t)R * per));
+  CUDA_OK(d_cnt_loc.alloc(ctx, (size_t)2 * per)); CUDA_OK(d_cnt_all.alloc(ctx, (size_t)R * 2 * per));
+  CUDA_OK(cudaMemsetAsync(d_loc.p, 0, d_loc.n * 8, ctx->stream));          // see bolt_spectra: early-stopped modes, uncarried partials
+  CUDA_OK(cudaMemsetAsync(d_st_loc.p, 0, per * sizeof(int), ctx->stream));
+  CUDA_OK(cudaMemsetAsync(d_cnt_loc.p, 0, (size_t)2 * per * sizeof(long long), ctx->stream));
+  bolt_opts oo = *o;
+  oo.ix_first = std::max(oo.ix_first, ix_start);
+  // K1 on the local shard (already in descending k: identity work order)
+  if (nloc) {
+    rc = launch_hierarchy(ctx, c, d_kloc.p, d_ident.p, nloc, &oo, d_loc.p, d_loc.p + (size_t)per * row, nullptr, nullptr, d_st_loc.p,
+                          d_cnt_loc.p, d_cnt_loc.p + per);
+    if (rc) return bail(ctx, rc);
+  }
+  // K2 prerequisites that do not depend on K1: the j_l tables of the local multipoles, on the second stream (fills K1's tail)
+  std::vector<int32_t> ell_loc;
+  for (int i = rank; i < nell; i += R) ell_loc.push_back(ell[i]);
+  const int nl = (int)ell_loc.size();
+  BesselTabs bt;
+  if (nl) { rc = bessel_prepare(ctx, c, ell_loc.data(), nl, kd_max, ctx->stream2, bt); if (rc) return bail(ctx, rc); }
+  // exchange 1: source columns (+ per-mode status and step counts, a few KB)
+  NCCL_OK(g_nccl.AllGather(d_loc.p, d_gath.p, (size_t)2 * per * row, NCCL_FLOAT64, ctx->comm, ctx->stream), "ncclAllGather(sources)");
+  NCCL_OK(g_nccl.AllGather(d_st_loc.p, d_st_all.p, (size_t)per, NCCL_INT32, ctx->comm, ctx->stream), "ncclAllGather(status)");
+  NCCL_OK(g_nccl.AllGather(d_cnt_loc.p, d_cnt_all.p, (size_t)2 * per, NCCL_INT64, ctx->comm, ctx->stream), "ncclAllGather(step counts)");
+  unshard_sources_kernel<<<nk, 256, 0, ctx->stream>>>(d_gath.p, d_order.p, nk, R, per, row, d_ST.p, d_SP.p);
+  CUDA_OK(cudaGetLastError());
+  // K2 on the local multipoles, scattered into the full (zeroed) C_l vector; exchange 2: one all-reduce
+  const size_t ncl = (size_t)nell * nd;
+  CUDA_OK(d_cl.alloc(ctx, 3 * ncl));
+  CUDA_OK(cudaMemsetAsync(d_cl.p, 0, 3 * ncl * 8, ctx->stream));
+  if (nl) {
+    CUDA_OK(d_cl_loc.alloc(ctx, (size_t)3 * nl * nd));
+    rc = project_device(ctx, c, d_ST.p, d_SP.p, d_k.p, nk, bt, nl, kd_min, kd_max, n_kd, ix_start, d_cl_loc.p);
+    if (rc) return bail(ctx, rc);
+    scatter_cl_kernel<<<(3 * nl * nd + 255) / 256, 256, 0, ctx->stream>>>(d_cl_loc.p, nl, nell, nd, rank, R, d_cl.p);
+    CUDA_OK(cudaGetLastError());
+  }
+  NCCL_OK(g_nccl.AllReduce(d_cl.p, d_cl.p, 3 * ncl, NCCL_FLOAT64, NCCL_SUM, ctx->comm, ctx->stream), "ncclAllReduce(C_l)");
+  if (cl_tt) CUDA_OK(cudaMemcpyAsync(cl_tt, d_cl.p, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_te) CUDA_OK(cudaMemcpyAsync(cl_te, d_cl.p + ncl, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cl_ee) CUDA_OK(cudaMemcpyAsync(cl_ee, d_cl.p + 2 * ncl, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<int> h_st((size_t)R * per); std::vector<long long> h_cnt((size_t)R * 2 * per);
+  CUDA_OK(cudaMemcpyAsync(h_st.data(), d_st_all.p, h_st.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(h_cnt.data(), d_cnt_all.p, h_cnt.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  for (int pos = 0; pos < nk; pos++) {
+    const int r = pos % R, j = pos / R, ik = order[pos];
+    if (status) status[ik] = h_st[(size_t)r * per + j];
+    if (nsteps) nsteps[ik] = h_cnt[((size_t)r * 2) * per + j];
+    if (nreject) nreject[ik] = h_cnt[((size_t)r * 2 + 1) * per + j];
+  }
   return collect_timing(ctx);
 }
 

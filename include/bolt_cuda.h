@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BOLT_ABI_VERSION 2
+#define BOLT_ABI_VERSION 3
 
 /* order of the scalar block (each entry nd doubles, value first) */
 enum bolt_scalar {
@@ -161,6 +161,25 @@ int  bolt_project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_S_T
                          const double* d_k, int nk, const int32_t* ell, int nell,
                          double kd_min, double kd_max, int n_kd, int ix_start,
                          double* d_cl /* [3][nell]: tt, te, ee */);
+
+/* Multi-GPU (one process per GPU, one context per process): the k-modes of ONE cosmology sharded over the ranks of a
+ * communicator -- what replaces the reference's threaded fan-out over k (src/spectra.jl:10, `tmap`) and over l
+ * (src/spectra.jl:149, `qmap`) when one GPU is not enough (BASELINE config 4).  NCCL is bound at run time.
+ *   bolt_comm_unique_id   rank 0 creates the 128-byte id; the HOST carries it to the other ranks (MPI.jl bcast,
+ *                         torch.distributed, a file): the only thing that crosses between processes outside NCCL.
+ *   bolt_comm_init        collective over all ranks.
+ *   bolt_spectra_sharded  same arguments and results as bolt_spectra on EVERY rank.  K1 on the rank's cyclic shard of the
+ *                         descending-k order, one ncclAllGather of the source columns, K2 on multipoles rank, rank+R, ...,
+ *                         ONE ncclAllReduce(sum, double) of the C_l vector; all on the context's stream.
+ *   bolt_shard_plan       (host only, no device needed) the indices into k[] that rank `rank` of `nranks` solves, in work order. */
+int  bolt_comm_unique_id(bolt_ctx* ctx, void* id128);
+int  bolt_comm_init(bolt_ctx* ctx, int rank, int nranks, const void* id128);
+int  bolt_comm_free(bolt_ctx* ctx);
+int  bolt_spectra_sharded(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
+                          const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start,
+                          double* cl_tt, double* cl_te, double* cl_ee,
+                          int32_t* status, int64_t* nsteps, int64_t* nreject);
+int  bolt_shard_plan(const double* k, int nk, int rank, int nranks, int32_t* idx, int32_t* n_local);
 
 #ifdef __cplusplus
 }

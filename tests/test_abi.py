@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert {"bolt_init", "bolt_solve", "bolt_project", "bolt_spectra", "bolt_plin", "bolt_cosmo_upload"} <= set(names)
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.bolt_abi_version() == 2
+    assert lib.bolt_abi_version() == 3
     assert lib.bolt_state_dim(8, 8, 10, 15) == 197 and lib.bolt_state_dim(50, 50, 20, 15) == 473
 
 
@@ -62,12 +62,17 @@ def test_no_cpu_fallback_without_device():
 def test_product_does_not_import_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may touch oracle/."""
     pkg = os.path.join(ROOT, "bolt.jl_b200")
-    pat = re.compile(r"(^|\s)(import\s+oracle|from\s+oracle)|oracle/|libbolt_oracle|OracleCosmo|dlopen")
+    pat = re.compile(r"(^|\s)(import\s+oracle|from\s+oracle)|oracle/|libbolt_oracle|OracleCosmo")
     for d, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".jl", ".h")):
                 txt = open(os.path.join(d, f)).read()
                 assert not pat.search(txt), os.path.join(d, f)
+                # run-time binding is allowed for NCCL only (bolt_comm_*): every library name handed to dlopen is an NCCL name
+                if "dlopen" in txt:
+                    names = re.search(r"const char\* names\[\] = \{([^}]*)\}", txt)
+                    assert names and all("nccl" in lit.lower() for lit in re.findall(r'"([^"]*)"', names.group(1))), os.path.join(d, f)
+                    assert len(re.findall(r"\bdlopen\(", txt)) == 1, os.path.join(d, f)
     # and bench.py touches it only inside its CPU-baseline legs: functions named cpu_* (the reported cpu_baseline and the
     # --impl reference arm both go through them), never at module level or inside the GPU arms
     import ast
@@ -84,3 +89,20 @@ def test_product_does_not_import_oracle():
             visit(ch, name)
     visit(tree, None)
     assert found and all(fn is not None and fn.startswith("cpu_") for fn in found), found
+
+
+def test_shard_plan_partitions_the_modes_in_work_order():
+    """bolt_shard_plan is host-only: cyclic shards of the descending-k order, disjoint and complete, equal to the Python mirror."""
+    import numpy as np
+    from bolt_b200 import capi
+    from bolt_b200.parallel import k_shard
+    rng = np.random.default_rng(5)
+    k = rng.random(37) + 0.1
+    for world in (1, 2, 3, 8):
+        seen = []
+        for r in range(world):
+            idx = capi.shard_plan(k, r, world)
+            assert np.all(np.diff(k[idx]) < 0)                      # work order: longest solves (largest k) first
+            assert np.array_equal(np.sort(idx), k_shard(k, r, world))
+            seen.append(idx)
+        assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(len(k)))
