@@ -215,6 +215,87 @@ def batch_arm(ctx, hcos, dcs, ells, ncos=4):
             "failed_modes": int((out[3] != 0).sum())}
 
 
+def strong_main(args, ctx, rank, world, local_rank, barrier):
+    """BASELINE configs[3]: high-resolution k-sweep of ONE cosmology -- 10^4 quadratic k-modes, l_gamma = 50 (state n = 281, the
+    runtime-truncation K1 path), adaptive 1e-11, full LOS projection l = 2..2500 -- sharded over the GPUs inside the library
+    (bolt_spectra_sharded).  Strong scaling: the total work is fixed, value = 10^4 / time per spectrum set."""
+    import torch
+    import torch.distributed as dist
+    from bolt_b200 import abi, capi
+    import bolt_b200 as B
+    NK4, LG4 = 10000, 50
+    par = synthetic_params(0)
+    bg = B.Background(par)
+    ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+    hc = abi.HostCosmo.from_host(par, bg, ih)
+    k = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, NK4)
+    ix0 = int(np.argmax(bg.x_grid > -8))
+    ells = np.arange(ELL_MIN, ELL_MAX + 1, dtype=np.int32)
+    o = abi.make_opts(LG4, 8, 10, reltol=RELTOL, abstol=ABSTOL)
+    n = abi.state_dim(LG4, 8, 10, 15)
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)        # NCCL's version banner goes to stderr
+        try:
+            ctx.comm_init_torch()
+        finally:
+            os.dup2(saved, 1); os.close(saved)
+    dc = capi.DeviceCosmo(ctx, hc)
+    call = (lambda d: d.spectra_sharded(k, o, ells, 0.01 * bg.H0, 1000 * bg.H0, 5000, ix0))
+
+    def step_e2e():
+        d = capi.DeviceCosmo(ctx, hc)        # H2D tables
+        out = call(d)                        # H2D k, ells; D2H C_l, status, step counts
+        d.close()
+        return out
+
+    for i in range(args.warmup):
+        call(dc)
+    fp64_peak = ctx.fp64_peak_tflops()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier(); t0 = time.perf_counter()
+    k1_ms = k2_ms = dev_ms = 0.0; launches = 0; attempts = 0; bad = 0
+    for i in range(args.steps):
+        tt, te, ee, st, ns = call(dc)
+        tm = ctx.timing(); k1_ms += tm["hierarchy_ms"]; k2_ms += tm["project_ms"]; dev_ms += tm["total_ms"]
+        launches += tm["hierarchy_launches"] + tm["bessel_launches"] + tm["project_launches"]
+        attempts += int(ns.sum() + dc.last_nreject.sum()); bad += int((st != 0).sum())
+    barrier(); wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    step_e2e(); barrier(); t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e()
+    barrier(); wall_e2e = time.perf_counter() - t0
+    times = torch.tensor([wall, wall_e2e, k1_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    wall, wall_e2e, k1_max = [float(v) for v in times.tolist()]
+    if rank == 0:
+        nell = len(ells)
+        fl = attempts / world * f_step(n)     # every rank reports the all-gathered counts of ALL modes: its own share is 1/N of them
+        line = {"metric": "kmode_hierarchy_solves_per_s", "value": NK4 * args.steps / wall, "unit": "k-mode solves/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C4: ONE cosmology, 10^4 quadratic k-modes (0.1 H0 .. 1000 H0), l_gamma = 50, l_nu = 8, l_mnu = 10 (n = 281), adaptive "
+                                       "KenCarp4 reltol 1e-11 / abstol 1e-6, TT+TE+EE C_l for l = 2..2500 on the 5000-point dense k grid",
+                           "parallelism": f"k-modes (K1) and multipoles (K2) sharded x{world} inside the library: ncclAllGather of the source columns "
+                                          "(320 MB), one ncclAllReduce of C_l (60 KB)",
+                           "l2": "no explicit flush: 320 MB of source grids + 200 MB of Bessel tables per step > 126 MB L2"},
+                "spectra_per_s": args.steps / wall, "kernel_ms_per_step_rank0": {"hierarchy": k1_ms / args.steps, "projection": k2_ms / args.steps,
+                                                                                  "device_total": dev_ms / args.steps},
+                "ode_step_attempts_per_solve": attempts / (NK4 * args.steps), "failed_modes": bad, "clocks": clocks, "gpu_launches": launches,
+                "roofline": {"kernel": "hierarchy_kernel_t<TruncRT> (K1, runtime truncations)", "bound": "fp64",
+                             "achieved": fl / (k1_max * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": fl / (k1_max * 1e-3) / 1e12 / fp64_peak if fp64_peak else None, "traffic": None,
+                             "note": "algorithmic flop = this rank's step attempts x (182 n + 3300), n = 281, over the slowest rank's K1 time"},
+                "e2e": {"value": NK4 * args.steps / wall_e2e, "unit": "k-mode solves/s",
+                        "h2d_bytes_per_step": int(world * (hc.tables.nbytes + hc.scalars.nbytes + 2 * 15 * 8 + NK4 * 8 + nell * 4)),
+                        "d2h_bytes_per_step": int(world * (3 * nell * 8 + NK4 * 4 + 2 * NK4 * 8))}}
+        print(json.dumps(line))
+    if world > 1:
+        ctx.comm_free()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,6 +304,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gradients", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): cosmology-sharded C3-value; strong: BASELINE configs[3] (10^4 k-modes, l_gamma = 50, ONE cosmology) "
+                         "with its k-modes and multipoles sharded over the GPUs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -270,6 +354,11 @@ def main():
         torch.cuda.synchronize()
 
     ctx = capi.Context(local_rank)
+    if args.scaling == "strong":
+        strong_main(args, ctx, rank, world, local_rank, barrier)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
     # N = 1: two synthetic cosmologies, alternated between steps.
     # N > 1: a pool of DISTINCT synthetic cosmologies behind a SHARED WORK QUEUE (an atomic counter in the rendezvous store):
     # the timed region is one batch of steps x N cosmologies (job j = pool[j % pool size]); a rank pulls the next job when it is
@@ -340,7 +429,12 @@ def main():
     # the ranks inside the library -- ncclAllGather of the source columns, one ncclAllReduce of C_l (bolt_spectra_sharded)
     strong = None
     if world > 1:
-        ctx.comm_init_torch()
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)        # NCCL prints its version banner on stdout: keep stdout to the ONE JSON line
+        try:
+            ctx.comm_init_torch()
+        finally:
+            os.dup2(saved, 1); os.close(saved)
         h, dc = hcos[0], dcs[0]
         o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL)
         kmin, kmax, nkd = h["kd"]
