@@ -283,11 +283,12 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   if (!force_generic && nq == 15 && p.Lnu == 8 && p.Lm == 10) {          // source_grid's truncations (src/spectra.jl:11)
     // Two kernels for source_grid's truncations.  The pipelined CTA-per-mode kernel (hierarchy_pipe.cuh) has 2.1-2.6x lower
     // per-mode latency (one mode: 12.9 vs 33.1 ms; 296 modes: 15.4 vs 33.1 ms) but holds only 2 modes per SM; the one-warp-per-mode
-    // kernel holds 8 and wins once the modes outnumber the resident CTAs several times (2000 modes: 59.6 vs 46.8 ms).
+    // kernel holds 8 and wins once the modes outnumber the resident CTAs several times (500 modes: 16.0 vs 34.1 ms, 1000: 30.5 vs 42.3,
+    // 1400: 41.5 vs 44.4, 2000: 59.6 vs 46.8 ms).
     // BOLT_K1_PIPE=1 / BOLT_K1_WARP=1 / BOLT_K1_CTA=1 (the first CTA kernel, kept for comparison) force one.
     if (p.L == 8 || p.L == 10) {
       if (getenv("BOLT_K1_CTA")) return launch_k1_cta(ctx, p);
-      if (getenv("BOLT_K1_PIPE") || (!getenv("BOLT_K1_WARP") && p.nk <= 8 * ctx->num_sms)) return launch_k1_pipe(ctx, p);
+      if (getenv("BOLT_K1_PIPE") || (!getenv("BOLT_K1_WARP") && p.nk <= 9 * ctx->num_sms)) return launch_k1_pipe(ctx, p);
     }
     if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15, K1_NCH>>(ctx, p);         // l_gamma = 8: the reference default
     if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15, K1_NCH>>(ctx, p);       // l_gamma = 10: BASELINE config 1
