@@ -65,6 +65,14 @@ class HostCosmo:
     def scalar(self, name):
         return self.scalars[S[name], 0]
 
+    def padded(self, nd):
+        """The same cosmology with all-zero partials appended up to `nd` components (the library instantiates its kernels for
+        1, 2, 3, 4 and 6 partials; 5 is served as 6 with a zero partial whose results are dropped by the binding)."""
+        assert nd >= self.nd
+        sc = np.zeros((NSCALARS, nd)); tb = np.zeros(self.tables.shape[:2] + (nd,))
+        sc[:, :self.nd] = self.scalars; tb[:, :, :self.nd] = self.tables
+        return HostCosmo(sc, self.quad_pts, self.quad_wts, tb, self.x0, self.dx)
+
     @staticmethod
     def from_host(par, bg, ih):
         """Pack Background + IonizationHistory (value only, nd = 1)."""

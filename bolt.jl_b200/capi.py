@@ -144,10 +144,27 @@ def spectra_batch(ctx, dcs, ks, opts, ells, kd_min, kd_max, n_kd, ix_start):
 class DeviceCosmo:
     """bolt_cosmo: the device-resident tables of one cosmology."""
 
+    SUPPORTED_NP = (0, 1, 2, 3, 4, 6)       # kernel instantiations of this build (partials per call)
+
     def __init__(self, ctx, host_cosmo):
+        # any number of partials up to 6: a count without its own instantiation (5) is padded with all-zero partials to the
+        # next one; `nd_user` components are handed back (the padded ones are identically zero and dropped)
+        self.nd_user = host_cosmo.nd
+        np_ = host_cosmo.nd - 1
+        if np_ not in self.SUPPORTED_NP:
+            bigger = [v for v in self.SUPPORTED_NP if v > np_]
+            if not bigger:
+                raise BoltError(f"{np_} partials per call: this build carries at most {self.SUPPORTED_NP[-1]}")
+            host_cosmo = host_cosmo.padded(1 + bigger[0])
         self.ctx, self.hc = ctx, host_cosmo
         self._h = C.c_void_p()
         ctx.check(lib().bolt_cosmo_upload(ctx._h, C.byref(host_cosmo.desc), C.byref(self._h)))
+
+    def _user(self, a):
+        """Drop padded partial components from a dual-capable result."""
+        if a is None or self.hc.nd == self.nd_user or a.ndim == 0 or a.shape[-1] != self.hc.nd:
+            return a
+        return np.ascontiguousarray(a[..., :self.nd_user]) if self.nd_user > 1 else np.ascontiguousarray(a[..., 0])
 
     def close(self):
         if self._h and self.ctx._h:
@@ -178,13 +195,21 @@ class DeviceCosmo:
                                         abi.ptr(out["S_P"]), abi.ptr(out["u_hist"]), abi.ptr(out["u_final"]),
                                         abi.ptr(out["status"], abi.c_int32_p), abi.ptr(out["nsteps"], abi.c_int64_p),
                                         abi.ptr(out["nreject"], abi.c_int64_p)))
+        for key in ("S_T", "S_P", "u_final"):
+            out[key] = self._user(out[key])
         return out
 
     def project(self, S_T, S_P, k, ells, kd_min, kd_max, n_kd, ix_start):
         k = np.ascontiguousarray(k, dtype=np.float64)
         ells = np.ascontiguousarray(ells, dtype=np.int32)
-        S_T = None if S_T is None else np.ascontiguousarray(S_T, dtype=np.float64)
-        S_P = None if S_P is None else np.ascontiguousarray(S_P, dtype=np.float64)
+        def widen(S):       # source grids coming back from the caller carry nd_user components: re-attach the zero padding
+            if S is None:
+                return None
+            S = np.ascontiguousarray(S, dtype=np.float64)
+            if self.hc.nd != self.nd_user and S.shape[-1] == self.nd_user:
+                S = np.concatenate([S, np.zeros(S.shape[:-1] + (self.hc.nd - self.nd_user,))], axis=-1)
+            return np.ascontiguousarray(S)
+        S_T, S_P = widen(S_T), widen(S_P)
         shp = (len(ells),) if self.hc.nd == 1 else (len(ells), self.hc.nd)
         tt = np.zeros(shp) if S_T is not None else None
         ee = np.zeros(shp) if S_P is not None else None
@@ -192,7 +217,7 @@ class DeviceCosmo:
         self.ctx.check(lib().bolt_project(self.ctx._h, self._h, abi.ptr(S_T), abi.ptr(S_P), abi.ptr(k), len(k),
                                           abi.ptr(ells, abi.c_int32_p), len(ells), kd_min, kd_max, n_kd, ix_start,
                                           abi.ptr(tt), abi.ptr(te), abi.ptr(ee)))
-        return tt, te, ee
+        return self._user(tt), self._user(te), self._user(ee)
 
     def spectra(self, k, opts, ells, kd_min, kd_max, n_kd, ix_start):
         k = np.ascontiguousarray(k, dtype=np.float64)
@@ -205,7 +230,7 @@ class DeviceCosmo:
                                           abi.ptr(tt), abi.ptr(te), abi.ptr(ee), abi.ptr(st, abi.c_int32_p),
                                           abi.ptr(ns, abi.c_int64_p), abi.ptr(nr, abi.c_int64_p)))
         self.last_nreject = nr          # rejected steps per mode of the last call (cost as much as accepted ones)
-        return tt, te, ee, st, ns
+        return self._user(tt), self._user(te), self._user(ee), st, ns
 
     def spectra_sharded(self, k, opts, ells, kd_min, kd_max, n_kd, ix_start):
         """bolt_spectra_sharded: collective over the ranks of the context's communicator (Context.comm_init)."""
@@ -219,7 +244,7 @@ class DeviceCosmo:
                                                   abi.ptr(tt), abi.ptr(te), abi.ptr(ee), abi.ptr(st, abi.c_int32_p),
                                                   abi.ptr(ns, abi.c_int64_p), abi.ptr(nr, abi.c_int64_p)))
         self.last_nreject = nr
-        return tt, te, ee, st, ns
+        return self._user(tt), self._user(te), self._user(ee), st, ns
 
     def plin(self, k, opts):
         k = np.ascontiguousarray(k, dtype=np.float64)
@@ -227,7 +252,7 @@ class DeviceCosmo:
         st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
         self.ctx.check(lib().bolt_plin(self.ctx._h, self._h, abi.ptr(k), len(k), C.byref(opts), abi.ptr(pk),
                                        abi.ptr(st, abi.c_int32_p), abi.ptr(ns, abi.c_int64_p)))
-        return pk, st, ns
+        return self._user(pk), st, ns
 
     # ---- device-pointer variants (torch tensors own the HBM buffers) ---------------------------------
     def solve_device(self, k_t, opts, want_final=False):

@@ -30,3 +30,16 @@ def test_amplitude_and_tilt_partials_need_no_host_rerun(cosmo, monkeypatch):
     assert dual.scalars[abi.S["A"], 1] == 1.0 or abs(dual.scalars[abi.S["A"], 1] - 1.0) < 1e-9
     assert abs(dual.scalars[abi.S["n"], 2] - 1.0) < 1e-9 and dual.scalars[abi.S["A"], 2] == 0.0
     assert not dual.tables[..., 1:].any()                    # the tables do not depend on A or n
+
+
+def test_partial_counts_without_an_instantiation_are_padded():
+    """5 partials per call are served by the 6-partial kernels with an all-zero partial (HostCosmo.padded)."""
+    import numpy as np
+    from bolt_b200 import abi
+    rng = np.random.default_rng(3)
+    nd, n_x, nq = 6, 7, 4
+    hc = abi.HostCosmo(rng.random((abi.NSCALARS, nd)), rng.random(nq), rng.random(nq), rng.random((abi.NTABLES, n_x + 2, nd)), -20.0, 0.01)
+    p = hc.padded(7)
+    assert p.nd == 7 and p.n_x == n_x and p.desc.nd == 7
+    assert np.array_equal(p.scalars[:, :6], hc.scalars) and np.all(p.scalars[:, 6] == 0)
+    assert np.array_equal(p.tables[:, :, :6], hc.tables) and np.all(p.tables[:, :, 6] == 0)
