@@ -27,6 +27,8 @@ using namespace bolt;
 namespace bolt {      // k1_cta.cu: the warp-specialised K1 (one CTA per k-mode), its own translation unit
 int k1_cta_init_constants();
 cudaError_t k1_cta_launch(const SolveParams& p, int num_sms, cudaStream_t st, int* grid_out);
+int k1_dual_cta_init_constants();  // k1_dual_cta.cu: K1 with partials, one CTA per mode (value warp + one warp per sensitivity system)
+cudaError_t k1_dual_cta_launch(const SolveParams& p, int np, int num_sms, cudaStream_t st);
 int k1_pipe_init_constants();      // k1_pipe.cu: the pipelined K1 (one CTA per k-mode, six warps by role)
 cudaError_t k1_pipe_launch(const SolveParams& p, int num_sms, cudaStream_t st, int* grid_out);
 }
@@ -61,6 +63,9 @@ struct bolt_cosmo {
   // K2 only) have identically zero sensitivities and are not carried through the ODE solve
   DevCosmo* d_k1 = nullptr; const DevCosmo** d_list_k1 = nullptr; double* d_dtables_k1 = nullptr;
   int np_k1 = 0; int map_k1[MAX_NP] = {0};
+  // single-partial views of the K1 cosmology (partial j moved to slot 0, np = 1): what a sensitivity warp of the CTA kernel
+  // with partials evaluates its Dual<1> background and G_j rows on (hierarchy_dual_cta.cuh)
+  DevCosmo h_k1; DevCosmo* d_views = nullptr; const DevCosmo** d_view_list = nullptr;
 };
 
 // DFMA throughput microbenchmark: 8 independent FMA chains per thread (the FP64 roofline denominator;
@@ -152,6 +157,7 @@ int init_constants(bolt_ctx* ctx) {
   CUDA_OK(cudaMemcpyToSymbol(c_rl1, rl1, sizeof(rl1)));
   if (k1_cta_init_constants()) return fail(ctx, BOLT_ERR_CUDA, "constant tables of k1_cta.cu");
   if (k1_pipe_init_constants()) return fail(ctx, BOLT_ERR_CUDA, "constant tables of k1_pipe.cu");
+  if (k1_dual_cta_init_constants()) return fail(ctx, BOLT_ERR_CUDA, "constant tables of k1_dual_cta.cu");
   g_const_init[ctx->device] = true;
   return BOLT_OK;
 }
@@ -248,8 +254,9 @@ int launch_k1_dual_reg(bolt_ctx* ctx, const SolveParams& p) {
 // cosmology g / nk_per.
 int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int np, int out_nd, const int* comp_map, int nk_per, const double* d_k, const int* d_order, int nk,
                      const bolt_opts* o, double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status,
-                     long long* d_nsteps, long long* d_nreject) {
+                     long long* d_nsteps, long long* d_nreject, const DevCosmo* const* view_list = nullptr) {
   SolveParams p;
+  p.view_list = view_list;
   p.cos_list = cos_list; p.nk_per = nk_per; p.k = d_k; p.order = d_order; p.nk = nk;
   p.L = o->l_gamma; p.Lnu = o->l_nu; p.Lm = o->l_mnu;
   p.n = bolt_state_dim(p.L, p.Lnu, p.Lm, nq);
@@ -263,6 +270,16 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
   if (np > 0) {     // value + gradient in one pass
     if (!getenv("BOLT_K1_GENERIC") && nq == 15 && p.L == 8 && p.Lnu == 8 && p.Lm == 10) {     // register-resident (hierarchy_dual_reg.cuh)
       typedef Trunc<8, 8, 10, 15, 19> TRD;
+      // one CTA per mode: the value system and every sensitivity system on a warp of their own, sharing the stage factorisation
+      // (hierarchy_dual_cta.cuh).  BOLT_K1_DUAL_WARP=1: the one-warp-per-mode kernel below.
+      if (p.view_list && !getenv("BOLT_K1_DUAL_WARP") && (np == 1 || np == 2 || np == 3 || np == 4 || np == 6)) {
+        CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+        CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        CUDA_OK(k1_dual_cta_launch(p, np, ctx->num_sms, ctx->stream));
+        CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        ctx->timing[4] += 1;
+        return BOLT_OK;
+      }
       switch (np) {
         case 1: return launch_k1_dual_reg<TRD, 1>(ctx, p);
         case 2: return launch_k1_dual_reg<TRD, 2>(ctx, p);
@@ -301,7 +318,8 @@ int launch_hierarchy(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, cons
                      double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status, long long* d_nsteps,
                      long long* d_nreject) {
   const bool compact = c->d_list_k1 != nullptr;
-  return launch_hierarchy(ctx, compact ? c->d_list_k1 : c->d_list, c->h.nq, c->np_k1, c->h.nd, c->map_k1, nk, d_k, d_order, nk, o, d_ST, d_SP, d_hist, d_final, d_status, d_nsteps, d_nreject);
+  return launch_hierarchy(ctx, compact ? c->d_list_k1 : c->d_list, c->h.nq, c->np_k1, c->h.nd, c->map_k1, nk, d_k, d_order, nk, o, d_ST, d_SP, d_hist, d_final, d_status, d_nsteps, d_nreject,
+                          c->d_view_list);
 }
 
 int upload_k_sorted(bolt_ctx* ctx, const double* k, int nk, DevBuf<double>& d_k, DevBuf<int>& d_order) {
@@ -649,6 +667,7 @@ int bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* d, bolt_cosmo** out)
           cudaMemcpy(c->d_k1, &k1, sizeof(DevCosmo), cudaMemcpyHostToDevice) != cudaSuccess) {
         bolt_cosmo_free(ctx, c); return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc/cudaMemcpy compact cosmology");
       }
+      c->h_k1 = k1;
       eta_end_kernel<<<1, 1, 0, ctx->stream>>>(c->d_k1);
       if (cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
           cudaMalloc(&c->d_list_k1, sizeof(DevCosmo*)) != cudaSuccess ||
@@ -658,6 +677,29 @@ int bolt_cosmo_upload(bolt_ctx* ctx, const bolt_cosmo_desc* d, bolt_cosmo** out)
     } else {
       c->np_k1 = np;
       for (int j = 0; j < np; j++) c->map_k1[j] = 1 + j;
+      c->h_k1 = h;
+    }
+    if (c->np_k1 > 0) {
+      const int na = c->np_k1;
+      std::vector<DevCosmo> views(na, c->h_k1);
+      for (int a = 0; a < na; a++) {
+        DevCosmo& v = views[a];
+        v.np = 1; v.nd = 2;
+        for (int t = 0; t < BOLT_NTABLES; t++) v.dtab[t] = c->h_k1.dtab[t] + (size_t)a * nc;
+        for (int i = 0; i < BOLT_NSCALARS; i++) v.ds[i][0] = c->h_k1.ds[i][a];
+        for (int i = 0; i < h.nq; i++) { v.dq[i][0] = c->h_k1.dq[i][a]; v.dwq[i][0] = c->h_k1.dwq[i][a]; }
+        v.dOmega_nu[0] = c->h_k1.dOmega_nu[a]; v.deta_end[0] = c->h_k1.deta_end[a];
+      }
+      std::vector<const DevCosmo*> vl(na);
+      if (cudaMalloc(&c->d_views, na * sizeof(DevCosmo)) != cudaSuccess ||
+          cudaMemcpy(c->d_views, views.data(), na * sizeof(DevCosmo), cudaMemcpyHostToDevice) != cudaSuccess) {
+        bolt_cosmo_free(ctx, c); return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc/cudaMemcpy single-partial views");
+      }
+      for (int a = 0; a < na; a++) vl[a] = c->d_views + a;
+      if (cudaMalloc(&c->d_view_list, na * sizeof(DevCosmo*)) != cudaSuccess ||
+          cudaMemcpy(c->d_view_list, vl.data(), na * sizeof(DevCosmo*), cudaMemcpyHostToDevice) != cudaSuccess) {
+        bolt_cosmo_free(ctx, c); return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc/cudaMemcpy view list");
+      }
     }
   }
   if (cudaMalloc(&c->d_list, sizeof(DevCosmo*)) != cudaSuccess) { cudaFree(c->d); cudaFree(c->d_tables); delete c; return fail(ctx, BOLT_ERR_ALLOC, "cudaMalloc list"); }
@@ -670,7 +712,7 @@ int bolt_cosmo_free(bolt_ctx* ctx, bolt_cosmo* c) {
   if (!c) return BOLT_OK;
   if (ctx) cudaSetDevice(ctx->device);
   cudaFree(c->d); cudaFree(c->d_tables); cudaFree(c->d_dtables); cudaFree(c->d_list);
-  cudaFree(c->d_k1); cudaFree(c->d_list_k1); cudaFree(c->d_dtables_k1);
+  cudaFree(c->d_k1); cudaFree(c->d_list_k1); cudaFree(c->d_dtables_k1); cudaFree(c->d_views); cudaFree(c->d_view_list);
   delete c;
   return BOLT_OK;
 }

@@ -49,6 +49,7 @@ struct SolveParams {
   int comp_map[MAX_NP];   // dual kernels: output slot (1-based partial index) of the kernel's partial j
   double* dbg;            // optional step log of mode 0: [dbg_cap][4] = x, dt, EEst, accepted
   int dbg_cap;
+  const DevCosmo* const* view_list;   // dual kernels, one cosmology: single-partial views [np] of the K1 cosmology (or null)
 };
 
 static __constant__ double c_rl[MAX_L + 1];   // l/(2l+1)

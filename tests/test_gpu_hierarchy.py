@@ -170,13 +170,25 @@ def test_long_chain_path_edge_truncations_match_oracle(cosmo, oracle, dev, trunc
         dev.solve(ks, abi.make_opts(3, 2, 3, fixed_dt=0.01), want=("u_hist",))
 
 
-def test_unsupported_partial_count_fails_loudly(cosmo, gpu_ctx):
-    """nd = 6 (five partials) is not instantiated in this build: the call must fail, never silently drop partials."""
+def test_partial_counts_without_an_instantiation(cosmo, gpu_ctx):
+    """Five partials have no kernel instantiation: the binding serves them through the six-partial kernels with an all-zero
+    partial and hands back five (tangent directions that are multiples of each other must give multiples).  More than six
+    fail loudly instead of silently dropping partials."""
     from bolt_b200 import abi, capi
     hc = cosmo.hc
     sc = np.zeros((abi.NSCALARS, 6)); tb = np.zeros(hc.tables.shape[:2] + (6,))
     sc[:, 0] = hc.scalars[:, 0]; tb[..., 0] = hc.tables[..., 0]
-    tb[..., 1:] = 1e-3 * hc.tables[..., :1]           # five non-trivial partials (all-zero partials would simply not be carried)
+    for j in range(5):
+        tb[..., 1 + j] = 1e-3 * (j + 1) * hc.tables[..., 0]           # five non-trivial partials
     dc = capi.DeviceCosmo(gpu_ctx, abi.HostCosmo(sc, hc.quad_pts, hc.quad_wts, tb, hc.x0, hc.dx))
+    assert dc.nd_user == 6 and dc.hc.nd == 7
+    out = dc.solve(np.array([10.0]) * cosmo.bg.H0, abi.make_opts(8, 8, 10, fixed_dt=0.05), want=("S_T", "u_final"))
+    assert out["status"][0] == 0 and out["S_T"].shape[-1] == 6 and out["u_final"].shape[-1] == 6
+    ref = out["u_final"][..., 1]
+    assert np.abs(ref).max() > 0
+    for j in range(1, 5):
+        assert np.abs(out["u_final"][..., 1 + j] - (j + 1) * ref).max() <= 1e-9 * np.abs(ref).max()
+    sc8 = np.zeros((abi.NSCALARS, 8)); tb8 = np.zeros(hc.tables.shape[:2] + (8,))
+    sc8[:, 0] = hc.scalars[:, 0]; tb8[..., 0] = hc.tables[..., 0]
     with pytest.raises(capi.BoltError, match="partials"):
-        dc.solve(np.array([10.0]) * cosmo.bg.H0, abi.make_opts(8, 8, 10, fixed_dt=0.05), want=("S_T",))
+        capi.DeviceCosmo(gpu_ctx, abi.HostCosmo(sc8, hc.quad_pts, hc.quad_wts, tb8, hc.x0, hc.dx))
