@@ -20,7 +20,38 @@
 namespace bolt {
 
 constexpr int BESSEL_NB = 5001;          // spectra.jl:53  (bessel_argmin:dg:bessel_argmax with dg = xmax/5000)
-constexpr int BESSEL_NC = BESSEL_NB + 2; // padded coefficients
+constexpr int BESSEL_NC = BESSEL_NB + 3; // ROW STRIDE of the coefficient tables: n+2 coefficients (Interpolations.jl padding) + one unused
+                                         // double, so that a row is 40032 bytes = a multiple of 16: the unit of a bulk (TMA) copy
+
+// Stage NL consecutive coefficient tables (rows e0.. of Cf, clamped at the last row) into shared memory with bulk asynchronous copies
+// (cp.async.bulk, the 1-D TMA path): one elected thread arms an mbarrier with the byte count and issues one 40 KB copy per table;
+// the copy engine moves the data while the CTA loads its other inputs; every thread then waits on the barrier.
+__device__ __forceinline__ void stage_tables_bulk(double* tabs, const double* __restrict__ Cf, int e0, int nell, int NL,
+                                                  unsigned long long* bar) {
+  const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned)(BESSEL_NC * sizeof(double));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes * (unsigned)NL) : "memory");
+    for (int l = 0; l < NL; l++) {
+      const int e = min(e0 + l, nell - 1);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(tabs + (size_t)l * BESSEL_NC);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(Cf + (size_t)e * BESSEL_NC), "r"(bytes), "r"(bar_s) : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void stage_tables_wait(unsigned long long* bar) {
+  const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar_s) : "memory");
+  }
+}
 
 // j_l(x) at x = i*dg for l in ells[] (ascending).  Miller's downward recurrence, normalised with the larger of
 // j_0, j_1; two passes so that rescaling never loses already-emitted values.  (SpecialFunctions.sphericalbesselj
@@ -147,18 +178,16 @@ struct ProjectParams {
 
 template <int NL, int NT>
 __global__ void __launch_bounds__(NT) project_kernel(ProjectParams p) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(128) double smem[];
   double* tabs = smem;                                   // [NL][BESSEL_NC]
   double* chi = smem + (size_t)NL * BESSEL_NC;           // [nrows]
   __shared__ double red[3 * NL][NT / 32];
+  __shared__ __align__(8) unsigned long long stage_bar;
   const int g = blockIdx.x, split = blockIdx.y;
   const int e0 = g * NL;
-  for (int idx = threadIdx.x; idx < NL * BESSEL_NC; idx += NT) {
-    const int l = idx / BESSEL_NC, o = idx - l * BESSEL_NC;
-    const int e = min(e0 + l, p.nell - 1);
-    tabs[idx] = p.Cf[(size_t)e * BESSEL_NC + o];
-  }
-  for (int i = threadIdx.x; i < p.nrows; i += NT) chi[i] = p.chi[i];
+  stage_tables_bulk(tabs, p.Cf, e0, p.nell, NL, &stage_bar);      // 160 KB by the copy engine ...
+  for (int i = threadIdx.x; i < p.nrows; i += NT) chi[i] = p.chi[i];   // ... while the threads fetch chi
+  stage_tables_wait(&stage_bar);
   __syncthreads();
 
   const int per = (p.nkd1 + p.nsplit - 1) / p.nsplit;
@@ -287,22 +316,20 @@ struct ProjectParamsD {
 template <int NL, int NT, int NP>
 __global__ void __launch_bounds__(NT) project_kernel_dual(ProjectParamsD pd) {
   const ProjectParams& p = pd.v;
-  extern __shared__ double smem[];
+  extern __shared__ __align__(128) double smem[];
   double* tabs = smem;                                   // [NL][BESSEL_NC]
   double* chi = smem + (size_t)NL * BESSEL_NC;           // [1+NP][nrows]
   __shared__ double red[3 * NL * (1 + NP)][NT / 32];
+  __shared__ __align__(8) unsigned long long stage_bar;
   const int g = blockIdx.x, split = blockIdx.y;
   const int e0 = g * NL;
-  for (int idx = threadIdx.x; idx < NL * BESSEL_NC; idx += NT) {
-    const int l = idx / BESSEL_NC, o = idx - l * BESSEL_NC;
-    const int e = min(e0 + l, p.nell - 1);
-    tabs[idx] = p.Cf[(size_t)e * BESSEL_NC + o];
-  }
+  stage_tables_bulk(tabs, p.Cf, e0, p.nell, NL, &stage_bar);
   for (int i = threadIdx.x; i < p.nrows; i += NT) {
     chi[i] = p.chi[i];
 #pragma unroll
     for (int q = 0; q < NP; q++) chi[(size_t)(1 + q) * p.nrows + i] = pd.chi_d[(size_t)q * p.nrows + i];
   }
+  stage_tables_wait(&stage_bar);
   __syncthreads();
   const int per = (p.nkd1 + p.nsplit - 1) / p.nsplit;
   const int jbeg = split * per, jend = min(p.nkd1, jbeg + per);

@@ -13,7 +13,8 @@ ctx = capi.Context(0); dc = capi.DeviceCosmo(ctx, abi.HostCosmo.from_host(par, b
 def run(which, ks, o, want):
     for nm in ("WARP", "CTA", "PIPE"):
         os.environ.pop("BOLT_K1_" + nm, None)
-    os.environ["BOLT_K1_" + which.upper()] = "1"
+    if which != "auto":          # auto: the library's own dispatch (pipe up to 9 x SMs modes, both kernels side by side beyond)
+        os.environ["BOLT_K1_" + which.upper()] = "1"
     out = dc.solve(ks, o, want=want)
     return out, ctx.timing()["hierarchy_ms"]
 
