@@ -33,7 +33,8 @@ GRAD_NAMES = ["Ω_b", "Ω_c", "h", "n", "A", "Σm_ν"]
 def synthetic_params(i):
     """Synthetic ΛCDM(+massive ν) parameter draws (SURVEY 8d ranges), deterministic in (SEED, i)."""
     import bolt_b200 as B
-    from bolt_b200.host import constants as K
+    import hostgen as HG
+    from hostgen import constants as K
     rng = np.random.default_rng([SEED, i])
     u = rng.random(6)
     return B.CosmoParams(h=0.60 + 0.20 * u[0], Ω_b=0.040 + 0.015 * u[1], Ω_c=0.20 + 0.10 * u[2], n=0.92 + 0.08 * u[3],
@@ -42,10 +43,11 @@ def synthetic_params(i):
 
 def make_host_cosmo(i):
     import bolt_b200 as B
+    import hostgen as HG
     from bolt_b200 import abi
     par = synthetic_params(i)
-    bg = B.Background(par)
-    ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+    bg = HG.Background(par)
+    ih = HG.IonizationHistory(HG.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
     hc = abi.HostCosmo.from_host(par, bg, ih)
     k = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, NK)
     ix_start = int(np.argmax(bg.x_grid > -8))
@@ -131,6 +133,7 @@ def cpu_sample_gradients(dual, bg, kstride=125):
     from bolt_b200 import abi
     from oracle.oracle import OracleCosmo, lib
     import bolt_b200 as B
+    import hostgen as HG
     lib().oracle_set_num_threads(host_threads())
     oc = OracleCosmo(dual)
     cores = lib().oracle_num_threads()
@@ -154,8 +157,9 @@ def gradient_arm(ctx, ells, with_cpu=True):
     the sixth direction is the neutrino mass.  One warm-up and three timed steps (host buffers: the e2e form), and the oracle's
     dual-number stepper on a bounded sample of the same workload as its CPU baseline."""
     import bolt_b200 as B
+    import hostgen as HG
     from bolt_b200 import abi, capi
-    from bolt_b200.api import host_cosmo_with_partials
+    from hostgen import host_cosmo_with_partials
     par = synthetic_params(0)
     dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, GRAD_NAMES, rel_step=1e-3)
     dc = capi.DeviceCosmo(ctx, dual)
@@ -188,6 +192,7 @@ def plin_arm(ctx, hcosmo, dc):
     """BASELINE configs[1]: linear matter P(k) via plin with massive neutrinos, 500 log-spaced k-modes, the reference's plin
     defaults l_gamma = l_nu = 50, l_mnu = 20 (state n = 473), reltol 1e-5 (src/spectra.jl:163-164).  Runtime-truncation K1 path."""
     import bolt_b200 as B
+    import hostgen as HG
     from bolt_b200 import abi
     bg = hcosmo["bg"]
     ks = B.log10_k(10 * bg.H0, 5000 * bg.H0, 500)
@@ -223,10 +228,11 @@ def strong_main(args, ctx, rank, world, local_rank, barrier):
     import torch.distributed as dist
     from bolt_b200 import abi, capi
     import bolt_b200 as B
+    import hostgen as HG
     NK4, LG4 = 10000, 50
     par = synthetic_params(0)
-    bg = B.Background(par)
-    ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+    bg = HG.Background(par)
+    ih = HG.IonizationHistory(HG.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
     hc = abi.HostCosmo.from_host(par, bg, ih)
     k = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, NK4)
     ix0 = int(np.argmax(bg.x_grid > -8))

@@ -2,7 +2,6 @@
 
 Import as `bolt_b200` (the directory name is not a Python identifier; see bolt_b200/__init__.py).
 """
-from .host.background import CosmoParams, Background          # noqa: F401
-from .host.recfast import RECFAST, IonizationHistory          # noqa: F401
+from .params import CosmoParams                               # noqa: F401
 from .api import (BasicNewtonian, Hierarchy, boltsolve, boltsolve_rsa, source_grid, source_grid_P,   # noqa: F401
                   quadratic_k, log10_k, cltt, clte, clee, plin, spectra, default_context, device_cosmo)

@@ -8,8 +8,7 @@ import threading
 import numpy as np
 
 from . import abi, capi
-from .host.background import CosmoParams, Background
-from .host.recfast import RECFAST, IonizationHistory
+from .params import CosmoParams
 
 
 class BasicNewtonian:
@@ -37,32 +36,6 @@ def device_cosmo(par, bg, ih, ctx=None):
     if key not in cache:
         cache[key] = capi.DeviceCosmo(ctx, abi.HostCosmo.from_host(par, bg, ih))
     return cache[key]
-
-
-def host_cosmo_with_partials(par, names, rel_step=1e-3, x_grid=None):
-    """Pack Background + IonizationHistory WITH partials d/d(par.<name>) for the device (nd = 1 + len(names)).
-
-    In Julia the partials come for free: Background / RECFAST run on ForwardDiff.Dual parameters and the spline
-    coefficient arrays are Vector{Dual}.  This Python host mirror has no AD, so it differentiates the host tables
-    by central differences of the whole host pipeline (2 extra host runs per parameter); what the device then does
-    with those partials (K1, K2, plin) is exact forward-mode propagation."""
-    def host(p):
-        bg = Background(p) if x_grid is None else Background(p, x_grid=x_grid)
-        ih = IonizationHistory(RECFAST(bg, OmegaB=p.Ω_b, Yp=p.Y_p, OmegaG=p.Ω_r), p, bg)
-        return abi.HostCosmo.from_host(p, bg, ih), bg, ih
-    base, bg, ih = host(par)
-    pm, steps = [], []
-    for nm in names:
-        v = getattr(par, nm)
-        dlt = rel_step * (abs(v) if v != 0 else 1.0)
-        if nm in ("A", "n"):      # enter only through the primordial weight (spectra.jl:92): no host re-run needed
-            hi = abi.HostCosmo(base.scalars.copy(), base.quad_pts, base.quad_wts, base.tables, base.x0, base.dx)
-            lo = abi.HostCosmo(base.scalars.copy(), base.quad_pts, base.quad_wts, base.tables, base.x0, base.dx)
-            hi.scalars[abi.S[nm], 0] = v + dlt; lo.scalars[abi.S[nm], 0] = v - dlt
-            pm.append((hi, lo)); steps.append(dlt)
-        else:
-            pm.append((host(par.replace(**{nm: v + dlt}))[0], host(par.replace(**{nm: v - dlt}))[0])); steps.append(dlt)
-    return abi.HostCosmo.with_partials(base, pm, steps), base, bg, ih, pm, steps
 
 
 def _check_status(status, where):
@@ -138,7 +111,7 @@ def rsa_perts(u, hierarchy, x):
     csb2 = ih.csb2(x)
     iN = 2 * (ℓᵧ + 1); iM = iN + ℓ_ν + 1; iS = iM + (h.ℓ_mν + 1) * nq
     Φ, δ, v, δ_b, v_b = u[iS:iS + 5]
-    from .host.background import q_grid, f0, dxdq
+    from .params import q_grid, f0, dxdq
     q, lqmi, lqma = q_grid(par, bg.quad_pts)
     eps = np.sqrt(q ** 2 + (a * par.Σm_ν) ** 2)
     w = f0(q, par) / dxdq(q, lqmi, lqma) * bg.quad_wts
@@ -332,7 +305,7 @@ def plin(k, par, bg, ih, n_q=15, ℓᵧ=50, ℓ_ν=50, ℓ_mν=20, x=0, reltol=1
 
 def _plin_from_state(u, k, par, bg, x, ℓᵧ, ℓ_ν, ℓ_mν):
     """The epilogue of plin (src/spectra.jl:170-197) on a state vector `u = perturb(x)`."""
-    from .host.background import q_grid, f0, dxdq
+    from .params import q_grid, f0, dxdq
     nq = bg.nq
     iM = 2 * (ℓᵧ + 1) + (ℓ_ν + 1); iS = iM + (ℓ_mν + 1) * nq
     q, lqmi, lqma = q_grid(par, bg.quad_pts)

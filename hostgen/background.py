@@ -1,4 +1,4 @@
-"""Host-side 1-D background (stays on the host per the north star; uploaded as spline tables).
+"""TEST / BENCH HARNESS (not product): host-side 1-D background, the input-table generator.
 
 Restates src/Bolt.jl:56-66 (CosmoParams) and src/background.jl:5-128.  All quantities are in
 the reference's Mpc units.  x = ln(a).
@@ -10,38 +10,7 @@ from . import constants as C
 from .bspline import CubicBSpline, spline_dx, spline_dx2
 
 
-@dataclass(frozen=True)
-class CosmoParams:
-    """src/Bolt.jl:56-66 (same field names; Σm_ν is in Mpc^-1 like the reference)."""
-    h: float = 0.7
-    Ω_r: float = 5.0469e-5
-    Ω_b: float = 0.046
-    Ω_c: float = 0.224
-    A: float = 2.097e-9
-    n: float = 1.0
-    Y_p: float = 0.24
-    N_ν: float = 3.046
-    Σm_ν: float = 0.06 * C.mass_natural
-
-    def replace(self, **kw):
-        return replace(self, **kw)
-
-    @staticmethod
-    def names():
-        return [f.name for f in fields(CosmoParams)]
-
-
-def H0(par):                                   # background.jl:5
-    return par.h * C.km_s_Mpc_100
-
-
-def rho_crit(par):                             # background.jl:6
-    return (3.0 / (8.0 * np.pi)) * H0(par) ** 2 / C.G_natural
-
-
-def T_nu(par):                                 # background.jl:22 (repeated all over the reference)
-    return (par.N_ν / 3.0) ** 0.25 * (4.0 / 11.0) ** (1.0 / 3.0) * \
-        (15.0 / np.pi ** 2 * rho_crit(par) * par.Ω_r) ** 0.25
+from bolt_b200.params import (CosmoParams, H0, rho_crit, T_nu, f0, dlnf0dlnq, to_ui, from_ui, dxdq, xq2q, q_grid)   # noqa: F401
 
 
 def Omega_Lambda(par):                         # background.jl:7-18
@@ -50,39 +19,6 @@ def Omega_Lambda(par):                         # background.jl:7-18
     Ω_ν = par.Σm_ν * νfac / par.h ** 2
     return 1.0 - (par.Ω_r * (1.0 + (2.0 / 3.0) * (7.0 * par.N_ν / 8.0) * (4.0 / 11.0) ** (4.0 / 3.0))
                   + par.Ω_b + par.Ω_c + Ω_ν)
-
-
-def f0(q, par):                                # background.jl:21-25
-    return 2.0 / (2.0 * np.pi) ** 3 / (np.exp(q / T_nu(par)) + 1.0)
-
-
-def dlnf0dlnq(q, par):                         # background.jl:27-30
-    Tν = T_nu(par)
-    return -q / Tν / (1.0 + np.exp(-q / Tν))
-
-
-# util.jl:24-27
-def to_ui(lq, lqmi, lqma):
-    return -1.0 + (1.0 - (-1.0)) / (lqma - lqmi) * (lq - lqmi)
-
-
-def from_ui(x, lqmi, lqma):
-    return lqmi + (lqma - lqmi) / (1.0 - (-1.0)) * (x - (-1.0))
-
-
-def dxdq(q, lqmi, lqma):
-    return (1.0 + to_ui(1.0 + lqmi, lqmi, lqma)) / (q * np.log(10.0))
-
-
-def xq2q(x, lqmi, lqma):
-    return 10.0 ** from_ui(x, lqmi, lqma)
-
-
-def q_grid(par, quad_pts):
-    """Momentum nodes q_i on [Tν/30, 30 Tν] (perturbations.jl:164-166)."""
-    Tν = T_nu(par)
-    lqmi, lqma = np.log10(Tν / 30.0), np.log10(Tν * 30.0)
-    return xq2q(quad_pts, lqmi, lqma), lqmi, lqma
 
 
 def rhoP_0(a, par, quad_pts, quad_wts):        # background.jl:33-48

@@ -3,11 +3,12 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bolt_b200 as B
+import hostgen as HG
 from bolt_b200 import abi, capi
 
 def host(par):
-    bg = B.Background(par)
-    ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+    bg = HG.Background(par)
+    ih = HG.IonizationHistory(HG.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
     return abi.HostCosmo.from_host(par, bg, ih), bg
 
 par = B.CosmoParams()

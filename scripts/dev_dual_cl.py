@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bolt_b200 as B
 from bolt_b200 import abi, capi
-from bolt_b200.api import host_cosmo_with_partials
+from hostgen import host_cosmo_with_partials
 par = B.CosmoParams(); ctx = capi.Context(0)
 for rel in (1e-5, 1e-4, 1e-3):
     dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, ["Ω_b"], rel_step=rel)

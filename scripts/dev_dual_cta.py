@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bolt_b200 as B
 from bolt_b200 import abi, capi
-from bolt_b200.api import host_cosmo_with_partials
+from hostgen import host_cosmo_with_partials
 
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["Ω_b", "Ω_c", "h", "Σm_ν"]
 sizes = [int(a) for a in sys.argv[2:]] or [200, 2000]

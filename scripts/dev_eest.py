@@ -3,10 +3,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 os.environ["BOLT_DEBUG_STEPS"] = "gpurun_out/gpu_steps.txt"
 import bolt_b200 as B
+import hostgen as HG
 from bolt_b200 import abi, capi
 from oracle.oracle import OracleCosmo
-par = B.CosmoParams(); bg = B.Background(par)
-ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+par = B.CosmoParams(); bg = HG.Background(par)
+ih = HG.IonizationHistory(HG.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
 hc = abi.HostCosmo.from_host(par, bg, ih)
 ctx = capi.Context(0); dc = capi.DeviceCosmo(ctx, hc)
 k = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 100)[int(sys.argv[1]):int(sys.argv[1]) + 1]
@@ -19,8 +20,8 @@ import numpy as np, pickle
 import bolt_b200 as B
 from bolt_b200 import abi
 from oracle.oracle import OracleCosmo
-par = B.CosmoParams(); bg = B.Background(par)
-ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+par = B.CosmoParams(); bg = HG.Background(par)
+ih = HG.IonizationHistory(HG.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
 oc = OracleCosmo(abi.HostCosmo.from_host(par, bg, ih))
 o = abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6)
 r = oc.solve(np.array([{float(k[0])!r}]), o, want=("S_T",)); print("oracle", r["nsteps"], r["nreject"])

@@ -2,8 +2,8 @@
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from bolt_b200.host.background import CosmoParams, Background
-from bolt_b200.host.recfast import RECFAST, IonizationHistory
+from hostgen.background import CosmoParams, Background
+from hostgen.recfast import RECFAST, IonizationHistory
 from bolt_b200 import abi, capi
 from oracle.oracle import OracleCosmo
 

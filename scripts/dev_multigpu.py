@@ -3,13 +3,14 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
 import bolt_b200 as B
+import hostgen as HG
 from bolt_b200 import abi, capi
 from bolt_b200.parallel import device_spectra_k_sharded
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-par = B.CosmoParams(); bg = B.Background(par)
-ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+par = B.CosmoParams(); bg = HG.Background(par)
+ih = HG.IonizationHistory(HG.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
 ctx = capi.Context(lr); dc = capi.DeviceCosmo(ctx, abi.HostCosmo.from_host(par, bg, ih))
 k = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 2000)
 ells = np.arange(2, 2501, dtype=np.int32)

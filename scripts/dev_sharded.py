@@ -8,6 +8,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 import bolt_b200 as B
+import hostgen as HG
 from bolt_b200 import abi, capi
 
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); lrank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -16,8 +17,8 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
 nk = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 lg = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-par = B.CosmoParams(); bg = B.Background(par)
-ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+par = B.CosmoParams(); bg = HG.Background(par)
+ih = HG.IonizationHistory(HG.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
 ctx = capi.Context(lrank)
 if world > 1:
     ctx.comm_init_torch()

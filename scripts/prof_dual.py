@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bolt_b200 as B
 from bolt_b200 import abi, capi
-from bolt_b200.api import host_cosmo_with_partials
+from hostgen import host_cosmo_with_partials
 nk = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 names = ["Ω_b", "Ω_c", "h", "Σm_ν"]
 par = B.CosmoParams()

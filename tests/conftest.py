@@ -23,11 +23,12 @@ class Cosmo:
 
     def __init__(self, **kw):
         import bolt_b200 as B
+        import hostgen as HG
         from bolt_b200 import abi
         self.par = B.CosmoParams(**kw)
-        self.bg = B.Background(self.par)
-        self.rec = B.RECFAST(self.bg, OmegaB=self.par.Ω_b, Yp=self.par.Y_p, OmegaG=self.par.Ω_r)
-        self.ih = B.IonizationHistory(self.rec, self.par, self.bg)
+        self.bg = HG.Background(self.par)
+        self.rec = HG.RECFAST(self.bg, OmegaB=self.par.Ω_b, Yp=self.par.Y_p, OmegaG=self.par.Ω_r)
+        self.ih = HG.IonizationHistory(self.rec, self.par, self.bg)
         self.hc = abi.HostCosmo.from_host(self.par, self.bg, self.ih)
         self.ix_start = int(np.argmax(self.bg.x_grid > -8))
 

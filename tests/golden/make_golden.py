@@ -45,10 +45,11 @@ def reference_fixtures():
 
 def oracle_vectors():
     import bolt_b200 as B
+    import hostgen as HG
     from bolt_b200 import abi
     from oracle.oracle import OracleCosmo
-    par = B.CosmoParams(); bg = B.Background(par)
-    ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+    par = B.CosmoParams(); bg = HG.Background(par)
+    ih = HG.IonizationHistory(HG.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
     hc = abi.HostCosmo.from_host(par, bg, ih); oc = OracleCosmo(hc)
     kg = B.quadratic_k(0.1 * bg.H0, 1000 * bg.H0, 100)
     o = abi.make_opts(8, 8, 10, reltol=1e-11, abstol=1e-6)
@@ -77,7 +78,8 @@ def bench_cosmology():
     """bench.py's synthetic cosmology #0 with partials (host generator + central differences, api.host_cosmo_with_partials)."""
     import bench
     import bolt_b200 as B
-    from bolt_b200.api import host_cosmo_with_partials
+    import hostgen as HG
+    from hostgen import host_cosmo_with_partials
     par = bench.synthetic_params(0)
     dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, GRAD_NAMES, rel_step=1e-3)
     return par, bg, dual, base
@@ -89,6 +91,7 @@ def _inputs(hc):
 
 def c3_value(par, bg, dual, base):
     import bolt_b200 as B
+    import hostgen as HG
     from bolt_b200 import abi
     from oracle.oracle import OracleCosmo
     oc = OracleCosmo(base)
@@ -105,6 +108,7 @@ def c3_value(par, bg, dual, base):
 
 def c3_grad(par, bg, dual, base, nk, name):
     import bolt_b200 as B
+    import hostgen as HG
     from bolt_b200 import abi
     from oracle.oracle import OracleCosmo
     od = OracleCosmo(dual)
@@ -123,6 +127,7 @@ def c3_grad(par, bg, dual, base, nk, name):
 
 def c2_plin(par, bg, dual, base):
     import bolt_b200 as B
+    import hostgen as HG
     from bolt_b200 import abi
     from oracle.oracle import OracleCosmo
     oc = OracleCosmo(base); od = OracleCosmo(dual)
@@ -137,6 +142,7 @@ def c2_plin(par, bg, dual, base):
 
 def c4_mini(par, bg, dual, base):
     import bolt_b200 as B
+    import hostgen as HG
     from bolt_b200 import abi
     from oracle.oracle import OracleCosmo
     oc = OracleCosmo(base)

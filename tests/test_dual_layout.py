@@ -20,7 +20,7 @@ def test_with_partials_layout_and_values(cosmo):
 
 
 def test_amplitude_and_tilt_partials_need_no_host_rerun(cosmo, monkeypatch):
-    import bolt_b200.api as api
+    import hostgen.partials as api
     from bolt_b200 import abi
     calls = []
     real = api.Background

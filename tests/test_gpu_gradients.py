@@ -15,7 +15,7 @@ NAMES = ["Ω_b", "h", "n"]
 def dual_setup(gpu_ctx):
     import bolt_b200 as B
     from bolt_b200 import capi
-    from bolt_b200.api import host_cosmo_with_partials
+    from hostgen import host_cosmo_with_partials
     par = B.CosmoParams()
     dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, NAMES, rel_step=1e-5)   # small step: k η₀ ~ 3000 makes the sources oscillatory in h
     dev = dict(dual=capi.DeviceCosmo(gpu_ctx, dual), base=capi.DeviceCosmo(gpu_ctx, base),
@@ -84,7 +84,7 @@ def test_amplitude_gradient_is_exact(gpu_ctx):
     """dC_ℓ/dA = C_ℓ/A and dP/dA = P/A exactly (spectra.jl:92,195)."""
     import bolt_b200 as B
     from bolt_b200 import abi, capi
-    from bolt_b200.api import host_cosmo_with_partials
+    from hostgen import host_cosmo_with_partials
     par = B.CosmoParams()
     dual, base, bg, ih, pm, steps = host_cosmo_with_partials(par, ["A"])
     dc = capi.DeviceCosmo(gpu_ctx, dual)

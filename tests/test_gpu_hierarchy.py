@@ -101,12 +101,13 @@ def test_other_momentum_grid_and_truncations(gpu_ctx):
     """Generality of the kernel beyond the reference defaults: nq = 8 momentum nodes (Background(par; nq=8)), uneven truncations,
     heavier neutrinos -- the generic (runtime-loop) path against the oracle."""
     import bolt_b200 as B
+    import hostgen as HG
     from bolt_b200 import abi, capi
-    from bolt_b200.host import constants as K
+    from hostgen import constants as K
     from oracle.oracle import OracleCosmo
     par = B.CosmoParams(Σm_ν=0.3 * K.mass_natural, h=0.65, Ω_c=0.27)
-    bg = B.Background(par, nq=8)
-    ih = B.IonizationHistory(B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
+    bg = HG.Background(par, nq=8)
+    ih = HG.IonizationHistory(HG.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r), par, bg)
     hc = abi.HostCosmo.from_host(par, bg, ih)
     assert hc.nq == 8
     dc = capi.DeviceCosmo(gpu_ctx, hc); oc = OracleCosmo(hc)

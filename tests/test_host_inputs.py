@@ -8,18 +8,19 @@ from conftest import load_golden
 def test_recfast_matches_fortran_golden():
     """test/runtests.jl:38-48: |Xe_fortran - Xe_RECFAST| < 1e-4 with CosmoParams(Σm_ν=0, N_ν=3, Ω_r=5.042e-5), Tnow=2.725."""
     import bolt_b200 as B
-    from bolt_b200.host.recfast import RecfastHistory
+    import hostgen as HG
+    from hostgen.recfast import RecfastHistory
     g = load_golden("recfast_xe.npz")
     par = B.CosmoParams(Σm_ν=0.0, N_ν=3.0, Ω_r=5.042e-5)
-    bg = B.Background(par)
-    r = B.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r, Tnow=2.725)
+    bg = HG.Background(par)
+    r = HG.RECFAST(bg, OmegaB=par.Ω_b, Yp=par.Y_p, OmegaG=par.Ω_r, Tnow=2.725)
     rh = RecfastHistory(r)
     mine = np.array([rh.Xe(z) for z in g["z"]])
     assert np.all(np.abs(mine - g["Xe"]) < 1e-4)
 
 
 def test_bspline_interpolates_and_has_natural_ends():
-    from bolt_b200.host.bspline import CubicBSpline
+    from hostgen.bspline import CubicBSpline
     x = np.linspace(-3.0, 2.0, 51)
     y = np.sin(x) + 0.1 * x ** 2
     s = CubicBSpline(y, x[0], x[1] - x[0])

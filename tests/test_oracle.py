@@ -29,7 +29,7 @@ def test_oracle_vs_class_phi_deltab(cosmo_nonu):
 
 def _mnu_check(cosmo, uh):
     """Φ, δ_b, δ_cdm and the massive-neutrino density contrast against CLASS (ncdm, no fluid approximation, reionization)."""
-    from bolt_b200.host.background import q_grid, f0, dxdq
+    from bolt_b200.params import q_grid, f0, dxdq
     g = load_golden("class_px_mnu.npz")
     par, bg = cosmo.par, cosmo.bg
     xg = bg.x_grid; n = uh.shape[1]
