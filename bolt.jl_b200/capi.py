@@ -16,7 +16,7 @@ _LIB = None
 EXPORTS = ["bolt_abi_version", "bolt_init", "bolt_finalize", "bolt_last_error", "bolt_last_timing",
            "bolt_cosmo_upload", "bolt_cosmo_free", "bolt_state_dim", "bolt_solve", "bolt_project",
            "bolt_spectra", "bolt_spectra_batch", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak", "bolt_set_bessel_xmax",
-           "bolt_comm_unique_id", "bolt_comm_init", "bolt_comm_free", "bolt_spectra_sharded", "bolt_shard_plan"]
+           "bolt_comm_unique_id", "bolt_comm_init", "bolt_comm_free", "bolt_spectra_sharded", "bolt_shard_plan", "bolt_fftlog"]
 
 
 class BoltError(RuntimeError):
@@ -56,6 +56,7 @@ def lib():
         L.bolt_comm_free.argtypes = [vp]
         L.bolt_spectra_sharded.argtypes = L.bolt_spectra.argtypes
         L.bolt_shard_plan.argtypes = [dp, C.c_int, C.c_int, C.c_int, ip, ip]
+        L.bolt_fftlog.argtypes = [vp, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, dp, dp, dp]
         _LIB = L
     return _LIB
 
@@ -292,3 +293,15 @@ def shard_plan(k, rank, nranks):
     if rc != 0:
         raise BoltError(f"bolt_shard_plan failed with {rc}")
     return idx[:int(n[0])].copy()
+
+
+def fftlog(ctx, r, a, mu, q, k0r0=1.0, kropt=True, inverse=False):
+    """bolt_fftlog: Bolt.plan_fftlog(r, mu, q, k0r0; kropt) followed by mul! (inverse=False) or ldiv! (src/util.jl:33-108).
+    Returns (y complex [N], k [N], k0r0 used)."""
+    r = np.ascontiguousarray(r, dtype=np.float64); a = np.asarray(a)
+    are = np.ascontiguousarray(a.real, dtype=np.float64)
+    aim = np.ascontiguousarray(a.imag, dtype=np.float64) if np.iscomplexobj(a) else None
+    y = np.zeros((len(r), 2)); k = np.zeros(len(r)); used = np.zeros(1)
+    ctx.check(lib().bolt_fftlog(ctx._h, abi.ptr(r), len(r), float(mu), float(q), float(k0r0), int(bool(kropt)), int(bool(inverse)),
+                                abi.ptr(are), abi.ptr(aim), abi.ptr(y), abi.ptr(k), abi.ptr(used)))
+    return y[:, 0] + 1j * y[:, 1], k, float(used[0])

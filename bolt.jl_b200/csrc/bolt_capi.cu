@@ -21,6 +21,7 @@
 #include "hierarchy_dual.cuh"
 #include "hierarchy_dual_reg.cuh"
 #include "projection_kernel.cuh"
+#include "fftlog.cuh"
 
 using namespace bolt;
 
@@ -1142,6 +1143,36 @@ int bolt_spectra_sharded(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, in
     if (nreject) nreject[ik] = h_cnt[((size_t)r * 2 + 1) * per + j];
   }
   return collect_timing(ctx);
+}
+
+// FFTLog (src/util.jl:33-108; pinned by the reference's test/runtests.jl:11-35 against test/data/fftlog_example.txt)
+int bolt_fftlog(bolt_ctx* ctx, const double* r, int N, double mu, double q, double k0r0, int kropt, int inverse,
+                const double* a_re, const double* a_im, double* y, double* k_out, double* k0r0_out) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (!r || !a_re || !y || N < 2 || N > 4096 || (N & (N - 1)) != 0) return fail(ctx, BOLT_ERR_ARG, "bolt_fftlog: N must be a power of two, 2 <= N <= 4096");
+  if (!(r[0] > 0.0) || !(r[N - 1] > r[0])) return fail(ctx, BOLT_ERR_ARG, "bolt_fftlog: r must be positive and increasing");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  const double logrmin = log(r[0]), logrmax = log(r[N - 1]);
+  const double L = logrmax - logrmin, dlnr = L / (N - 1), r0 = exp((logrmin + logrmax) / 2.0);       // plan_fftlog, util.jl:47-54
+  if (kropt) k0r0 = fftlog_k0r0_low_ringing(N, mu, q, L, k0r0);
+  if (k0r0_out) *k0r0_out = k0r0;
+  if (k_out) {       // k = reverse(k0 exp(n L / N)), n = range(-N/2, N/2, length = N)        (util.jl:58-60)
+    const double k0 = k0r0 / r0, nh = (double)(N / 2);
+    for (int i = 0; i < N; i++) { const double n = -nh + (2.0 * nh) * (double)i / (double)(N - 1); k_out[N - 1 - i] = k0 * exp(n * L / N); }
+  }
+  int lg = 0; while ((1 << lg) < N) lg++;
+  DevBuf<double> d_r, d_are, d_aim, d_y;
+  CUDA_OK(d_r.alloc(ctx, N)); CUDA_OK(d_are.alloc(ctx, N)); CUDA_OK(d_y.alloc(ctx, 2 * (size_t)N));
+  CUDA_OK(cudaMemcpyAsync(d_r.p, r, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(d_are.p, a_re, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (a_im) { CUDA_OK(d_aim.alloc(ctx, N)); CUDA_OK(cudaMemcpyAsync(d_aim.p, a_im, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); }
+  CUDA_OK(cudaFuncSetAttribute(fftlog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int)sizeof(double2)));
+  fftlog_kernel<<<1, std::min(N, 512), (size_t)N * sizeof(double2), ctx->stream>>>(d_r.p, N, lg, mu, q, dlnr, k0r0, inverse, d_are.p,
+                                                                                  a_im ? d_aim.p : nullptr, reinterpret_cast<double2*>(d_y.p));
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(y, d_y.p, 2 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return BOLT_OK;
 }
 
 int bolt_fp64_peak(bolt_ctx* ctx, double* tflops) {

@@ -352,4 +352,16 @@ function spectra_sharded(‚Ñì‚Éó, ùï°::AbstractCosmoParams{T}, bg, ih, k_grid; ‚
     end
 end
 
+"""FFTLog on the device (src/util.jl:33-108): `plan_fftlog(r, Œº, q, k‚ÇÄr‚ÇÄ; kropt)` followed by `mul!` (inverse = false) or `ldiv!`.
+Returns (y::Vector{ComplexF64}, k::Vector{Float64}).  N must be a power of two ‚â§ 4096."""
+function fftlog(r::AbstractVector, a::AbstractVector, Œº, q, k‚ÇÄr‚ÇÄ=1.0; kropt=true, inverse=false, dev=Device())
+    ctx = context(dev.ordinal); N = length(r)
+    rr = Float64.(r); are = Float64.(real.(a)); aim = Float64.(imag.(a))
+    y = zeros(Float64, 2, N); k = zeros(Float64, N); used = zeros(Float64, 1)
+    GC.@preserve rr are aim y k used check(ctx, ccall((:bolt_fftlog, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Cdouble, Cdouble, Cdouble, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        ctx, rr, N, Œº, q, k‚ÇÄr‚ÇÄ, kropt ? 1 : 0, inverse ? 1 : 0, are, aim, y, k, used))
+    complex.(y[1, :], y[2, :]), k
+end
+
 end # module

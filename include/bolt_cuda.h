@@ -181,6 +181,13 @@ int  bolt_spectra_sharded(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, i
                           int32_t* status, int64_t* nsteps, int64_t* nreject);
 int  bolt_shard_plan(const double* k, int nk, int rank, int nranks, int32_t* idx, int32_t* n_local);
 
+/* FFTLog (src/util.jl:33-108: plan_fftlog + mul! / ldiv!), SURVEY 8f row n4: the biased Hankel-type transform of a[N] sampled on
+ * the log-spaced grid r[N] (N a power of two <= 4096), order mu, bias q.  kropt != 0 applies k0r0_low_ringing (util.jl:79-89).
+ * inverse = 0: mul! (multiply by u_m), 1: ldiv! (divide).  a_im may be NULL.  y is [N][2] (re, im); k_out [N] (the output
+ * abscissae, may be NULL); k0r0_out the value actually used (may be NULL).  Not used by any spectrum function. */
+int  bolt_fftlog(bolt_ctx* ctx, const double* r, int N, double mu, double q, double k0r0, int kropt, int inverse,
+                 const double* a_re, const double* a_im, double* y, double* k_out, double* k0r0_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,7 +48,7 @@ int main() {
   double* out; long long* cyc; cudaMalloc(&out, 8 * 1024 * 64); cudaMalloc(&cyc, 8 * 16);
   const int n = 4096;
   const char* names[12] = {"DFMA dep", "DADD dep", "4xDFMA indep (per 4)", "LDS dep", "SHFL64+DADD dep", "fast_rcp+DADD dep", "exp+DADD dep", "sqrt(+DADD) dep", "1/x dep", "warp_sum+DMUL", "FFMA dep", "log dep"};
-  for (int warps = 1; warps <= 4; warps *= 2) {
+  for (int warps = 1; warps <= 32; warps *= 2) {
     k<<<1, 32 * warps>>>(out, cyc, 0.999999, 1e-9, n); cudaDeviceSynchronize();
     k<<<1, 32 * warps>>>(out, cyc, 0.999999, 1e-9, n); cudaDeviceSynchronize();
     long long h[16]; cudaMemcpy(h, cyc, 8 * 16, cudaMemcpyDeviceToHost);

@@ -37,6 +37,8 @@ def reference_fixtures():
     pk = np.loadtxt(f"{REF}/camb_pk_x0.dat")                  # k [h/Mpc], P(k) [(Mpc/h)^3] at z = 0; no reference test consumes it
     sel = np.arange(0, pk.shape[1], 20)
     np.savez_compressed(f"{HERE}/camb_pk.npz", k_h=pk[0, sel], pk_h3=pk[1, sel])
+    ff = np.loadtxt(f"{REF}/fftlog_example.txt")              # FFTLog known-answer vector (pyfftlog), test/runtests.jl:11-35
+    np.savez_compressed(f"{HERE}/fftlog_example.npz", k=ff[:, 0], f=ff[:, 1])
     camb = np.loadtxt(f"{REF}/camb_rough_ttteee_unlensed.dat")
     ells = np.arange(10, 2501, 10)
     np.savez_compressed(f"{HERE}/camb_cl.npz", ell=ells, tt=np.interp(ells, camb[0], camb[1]),
