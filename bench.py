@@ -203,6 +203,26 @@ def plin_arm(ctx, hcosmo, dc):
             "hierarchy_ms": ctx.timing()["hierarchy_ms"], "ode_steps_per_solve": float(ns.mean()), "failed_modes": int((st != 0).sum())}
 
 
+def hostgen_arm(local_rank, ncos=256):
+    """the input tables (background, RECFAST, reionization, optical depth and their spline coefficients) of a BATCH of
+    synthetic cosmologies on the device (bolt_hostgen_batch: one thread integrates the recombination ODEs of one cosmology), beside
+    the Python harness generator on one host core (the reference computes them on the host too, one cosmology at a time)."""
+    import hostgen as HG
+    from bolt_b200 import capi
+    pars = [synthetic_params(i) for i in range(ncos)]
+    capi.hostgen_batch(pars[:2], device=local_rank)
+    t0 = time.perf_counter(); hcs, st = capi.hostgen_batch(pars, device=local_rank); dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    bg = HG.Background(pars[0]); HG.IonizationHistory(HG.RECFAST(bg, OmegaB=pars[0].Ω_b, Yp=pars[0].Y_p, OmegaG=pars[0].Ω_r), pars[0], bg)
+    t_cpu = time.perf_counter() - t0
+    return {"workload": f"input tables of {ncos} synthetic cosmologies in one call (12 spline tables x 2003 coefficients + 13 scalars each, "
+                        "returned to host buffers)", "ms_per_call": 1e3 * dt, "ms_per_cosmology": 1e3 * dt / ncos, "cosmologies_per_s": ncos / dt,
+            "failed": int((st != 0).sum()),
+            "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "cosmologies/s", "cores": 1, "kind": "port",
+                             "sample": f"one cosmology through the Python harness generator hostgen/ ({t_cpu:.2f} s)"},
+            "speedup_vs_cpu_baseline": (ncos / dt) * t_cpu}
+
+
 def batch_arm(ctx, hcos, dcs, ells, ncos=4):
     """SURVEY 8d C5 (emulator / MCMC batches): the same C3-value workload through bolt_spectra_batch, ncos cosmologies per call --
     all ncos x 2000 hierarchy solves in ONE launch, so the tail of the persistent kernel is paid once per batch."""
@@ -524,6 +544,7 @@ def main():
         if world == 1:
             line["plin"] = guarded(plin_arm, ctx, hcos[0], dcs[0])
             line["batch"] = guarded(batch_arm, ctx, hcos, dcs, ells)
+            line["hostgen"] = guarded(hostgen_arm, local_rank)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

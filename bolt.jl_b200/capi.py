@@ -16,7 +16,8 @@ _LIB = None
 EXPORTS = ["bolt_abi_version", "bolt_init", "bolt_finalize", "bolt_last_error", "bolt_last_timing",
            "bolt_cosmo_upload", "bolt_cosmo_free", "bolt_state_dim", "bolt_solve", "bolt_project",
            "bolt_spectra", "bolt_spectra_batch", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak", "bolt_set_bessel_xmax",
-           "bolt_comm_unique_id", "bolt_comm_init", "bolt_comm_free", "bolt_spectra_sharded", "bolt_shard_plan", "bolt_fftlog"]
+           "bolt_comm_unique_id", "bolt_comm_init", "bolt_comm_free", "bolt_spectra_sharded", "bolt_shard_plan", "bolt_fftlog",
+           "bolt_hostgen_batch", "bolt_hostgen_last_error"]
 
 
 class BoltError(RuntimeError):
@@ -56,6 +57,8 @@ def lib():
         L.bolt_comm_free.argtypes = [vp]
         L.bolt_spectra_sharded.argtypes = L.bolt_spectra.argtypes
         L.bolt_shard_plan.argtypes = [dp, C.c_int, C.c_int, C.c_int, ip, ip]
+        L.bolt_hostgen_batch.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, C.c_int, dp, dp, ip]
+        L.bolt_hostgen_last_error.restype = C.c_char_p
         L.bolt_fftlog.argtypes = [vp, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, dp, dp, dp]
         _LIB = L
     return _LIB
@@ -305,3 +308,20 @@ def fftlog(ctx, r, a, mu, q, k0r0=1.0, kropt=True, inverse=False):
     ctx.check(lib().bolt_fftlog(ctx._h, abi.ptr(r), len(r), float(mu), float(q), float(k0r0), int(bool(kropt)), int(bool(inverse)),
                                 abi.ptr(are), abi.ptr(aim), abi.ptr(y), abi.ptr(k), abi.ptr(used)))
     return y[:, 0] + 1j * y[:, 1], k, float(used[0])
+
+
+def hostgen_batch(pars, x0=-20.0, dx=0.01, n_x=2001, nq=15, device=0):
+    """bolt_hostgen_batch: the input tables of a BATCH of cosmologies computed on the device (background, RECFAST, reionization,
+    optical depth, visibility, baryon sound speed and their spline coefficients).  pars: list of CosmoParams.
+    Returns (list of abi.HostCosmo ready for DeviceCosmo, status [ncos])."""
+    names = ["h", "Ω_r", "Ω_b", "Ω_c", "A", "n", "Y_p", "N_ν", "Σm_ν"]
+    P = np.ascontiguousarray([[getattr(p, nm) for nm in names] for p in pars], dtype=np.float64)
+    ncos = len(pars)
+    pts, wts = np.polynomial.legendre.leggauss(nq)           # FastGaussQuadrature.gausslegendre(nq), background.jl:105
+    pts = np.ascontiguousarray(pts); wts = np.ascontiguousarray(wts)
+    tabs = np.zeros((ncos, abi.NTABLES, n_x + 2)); sc = np.zeros((ncos, abi.NSCALARS)); st = np.zeros(ncos, dtype=np.int32)
+    rc = lib().bolt_hostgen_batch(int(device), abi.ptr(P), ncos, float(x0), float(dx), int(n_x), abi.ptr(pts), abi.ptr(wts), int(nq),
+                                  abi.ptr(tabs), abi.ptr(sc), abi.ptr(st, abi.c_int32_p))
+    if rc != 0:
+        raise BoltError(f"bolt_hostgen_batch failed with {rc}: {lib().bolt_hostgen_last_error().decode()}")
+    return [abi.HostCosmo(sc[i][:, None], pts, wts, tabs[i][:, :, None], x0, dx) for i in range(ncos)], st

@@ -188,6 +188,18 @@ int  bolt_shard_plan(const double* k, int nk, int rank, int nranks, int32_t* idx
 int  bolt_fftlog(bolt_ctx* ctx, const double* r, int N, double mu, double q, double k0r0, int kropt, int inverse,
                  const double* a_re, const double* a_im, double* y, double* k_out, double* k0r0_out);
 
+/* Batched input tables on the device: Background + RECFAST + reionization + optical depth for ncos cosmologies
+ * at once -- what the reference computes on the host one cosmology at a time (src/background.jl:5-128,
+ * src/ionization/recfast.jl:22-536, 674-726, src/ionization/ionization.jl:107-137).  params is [ncos][9] in CosmoParams order
+ * (h, Omega_r, Omega_b, Omega_c, A, n, Y_p, N_nu, Sum_m_nu; src/Bolt.jl:56-66); the x grid is x0 + dx*(0..n_x-1); quad_pts/quad_wts
+ * the Gauss-Legendre rule of Background (background.jl:105).  Output, caller-owned HOST buffers in the layout bolt_cosmo_desc
+ * points at (nd = 1): tables_out [ncos][BOLT_NTABLES][n_x+2], scalars_out [ncos][BOLT_NSCALARS]; status_out [ncos] (0 = ok,
+ * 1 = the recombination integrator gave up) may be NULL.  Value-only.  No context: the call selects `device_ordinal` itself. */
+int  bolt_hostgen_batch(int device_ordinal, const double* params, int ncos, double x0, double dx, int n_x,
+                        const double* quad_pts, const double* quad_wts, int nq,
+                        double* tables_out, double* scalars_out, int32_t* status_out);
+const char* bolt_hostgen_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif
