@@ -173,6 +173,26 @@ int check_opts(bolt_ctx* ctx, const bolt_cosmo* c, const bolt_opts* o) {
   return BOLT_OK;
 }
 
+// the one-warp-per-mode kernel with WPB warps per block in lockstep (hierarchy_kernel_t's header)
+template <class TR, int WPB>
+int launch_k1_lockstep(bolt_ctx* ctx, const SolveParams& p) {
+  auto kern = hierarchy_kernel_t<TR, WPB>;
+  const size_t smem = WPB * ((size_t)k1_num_arrays<TR>() * k1_array_len<TR>(p.n) + k1_extra_doubles<TR>()) * sizeof(double);
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int occ = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WPB, smem));
+  if (occ < 1) return fail(ctx, BOLT_ERR_UNSUPPORTED, "state does not fit in shared memory");
+  const int grid = std::max(1, std::min((p.nk + WPB - 1) / WPB, occ * ctx->num_sms));
+  CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  kern<<<grid, 32 * WPB, smem, ctx->stream>>>(p);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->timing[4] += 1;
+  return BOLT_OK;
+}
+
 template <class TR>
 int launch_k1(bolt_ctx* ctx, const SolveParams& p) {
   auto kern = hierarchy_kernel_t<TR>;
@@ -307,6 +327,16 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
     if (p.L == 8 || p.L == 10) {
       if (getenv("BOLT_K1_CTA")) return launch_k1_cta(ctx, p);
       if (getenv("BOLT_K1_PIPE") || (!getenv("BOLT_K1_WARP") && p.nk <= 9 * ctx->num_sms)) return launch_k1_pipe(ctx, p);
+    }
+    // Beyond that the one-warp-per-mode kernel, four warps per block in lockstep at stage granularity (shared instruction-cache
+    // fills: 592 / 1184 / 2000 modes 36.4 / 42.4 / 45.9 ms against 36.7 / 46.2 / 49.9 ms for independent warps, same box;
+    // 2 warps 35.3 / 42.5 / 48.7, 8 warps 44.9 / 44.8 / 49.5).  BOLT_K1_WPB=1: independent warps.
+    {
+      const int wpb = getenv("BOLT_K1_WPB") ? atoi(getenv("BOLT_K1_WPB")) : 4;
+      if (p.L == 8 && wpb == 4) return launch_k1_lockstep<Trunc<8, 8, 10, 15, K1_NCH>, 4>(ctx, p);
+      if (p.L == 10 && wpb == 4) return launch_k1_lockstep<Trunc<10, 8, 10, 15, K1_NCH>, 4>(ctx, p);
+      if (p.L == 8 && wpb == 2) return launch_k1_lockstep<Trunc<8, 8, 10, 15, K1_NCH>, 2>(ctx, p);
+      if (p.L == 8 && wpb == 8) return launch_k1_lockstep<Trunc<8, 8, 10, 15, K1_NCH>, 8>(ctx, p);
     }
     if (p.L == 8) return launch_k1<Trunc<8, 8, 10, 15, K1_NCH>>(ctx, p);         // l_gamma = 8: the reference default
     if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15, K1_NCH>>(ctx, p);       // l_gamma = 10: BASELINE config 1

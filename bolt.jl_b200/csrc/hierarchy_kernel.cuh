@@ -1072,19 +1072,27 @@ __host__ __device__ constexpr int k1_extra_doubles() { return TR::MAXLEN > 0 ? (
 #ifndef K1_MINBLOCKS
 #define K1_MINBLOCKS 8
 #endif
-template <class TR>
-__global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolveParams p) {
-  extern __shared__ double sm[];
+// WPB > 1 (register-resident truncations only): WPB warps per block, each still owning its own k-mode, kept in LOCKSTEP at stage
+// granularity by one named barrier at the top of every stage.  The kernel is instruction-fetch bound when its warps roam
+// independently through the 61 KB step loop (ncu, profiles/r2/k1_warp_occupancy_sweep.md: stall_no_inst 2 % with one warp per
+// SM, 10 % with four, 18 % with eight): every stage executes the same 25 KB of code, so warps that enter it together share the
+// instruction-cache fills.  A warp that runs out of work keeps arriving at the barrier until every warp of the block has.
+template <class TR, int WPB = 1>
+__global__ void __launch_bounds__(32 * WPB, (K1_MINBLOCKS / WPB > 0 ? K1_MINBLOCKS / WPB : 1)) hierarchy_kernel_t(SolveParams p) {
+  extern __shared__ double sm_all[];
+  __shared__ int nghost;
   constexpr int NCH = TR::NCH, MAXLEN = TR::MAXLEN;
   const int n = p.n;
   const int na = k1_array_len<TR>(n);
+  double* const sm = sm_all + (size_t)(threadIdx.x >> 5) * ((size_t)k1_num_arrays<TR>() * na + k1_extra_doubles<TR>());
   Lane ln;
   const bool fixed = (p.mode == BOLT_MODE_FIXED);
   const double reltol = p.reltol, abstol = p.abstol;
+  if constexpr (WPB > 1) { if (threadIdx.x == 0) nghost = 0; __syncthreads(); }
 
   while (true) {
     int w = 0;
-    if (threadIdx.x == 0) w = atomicAdd(p.counter, 1);
+    if ((threadIdx.x & 31) == 0) w = atomicAdd(p.counter, 1);
     w = __shfl_sync(FULL, w, 0);
     if (w >= p.nk) break;
     const int ik = p.order[w];
@@ -1194,6 +1202,7 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
         constexpr bool FLAT = (NCH == TR::NQ + 4);
         const bool live = (NCH == 32) || FLAT || ln.kind != CH_IDLE;
         for (int s = 1; s <= 6; s++) {
+          if constexpr (WPB > 1) asm volatile("bar.sync 1, %0;" ::"r"(32 * WPB) : "memory");      // lockstep (see the kernel's header)
           // z slot of this stage: Z1 and Z5 swap physical slots with the step parity, Z2..Z4 sit at slots 3..5
           double* zout = sm + (size_t)((s == 1) ? (flipU ? 0 : 2) : (s >= 5) ? (flipZ ? 1 : 6) : s + 1) * na;
           if (s <= 5) {
@@ -1450,6 +1459,14 @@ __global__ void __launch_bounds__(32, K1_MINBLOCKS) hierarchy_kernel_t(SolvePara
       if (p.nreject) p.nreject[ik] = nreject;
     }
     __syncwarp();
+  }
+  if constexpr (WPB > 1) {
+    // out of work: keep the block's barrier complete until every warp is
+    if ((threadIdx.x & 31) == 0) atomicAdd(&nghost, 1);
+    while (true) {
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * WPB) : "memory");
+      if (*(volatile int*)&nghost == WPB) break;
+    }
   }
 }
 
