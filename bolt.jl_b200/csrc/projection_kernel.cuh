@@ -202,7 +202,14 @@ __global__ void __launch_bounds__(NT) project_kernel(ProjectParams p) {
 #pragma unroll
     for (int l = 0; l < NL; l++) { th[l] = 0; ep[l] = 0; }
     const double* sT = p.SD_T + j; const double* sP = p.SD_P + j;
-#pragma unroll 2
+    // Sliding window over the four spline coefficients: chi_i decreases with i, so the table cell ii never increases, and for
+    // most (k, x) pairs it moves by 0-2 cells between consecutive rows (it moves by ks * dchi / dg).  The kernel is bound by its
+    // shared-memory gathers (8 wavefronts per warp-evaluation are bytes), so the coefficients that stay are kept in registers
+    // and only the new ones are fetched; adjacent k share the slide to within one cell, so the cases barely diverge in a warp.
+    // Same operands, same operation order: bit-identical to fetching all four every time.
+    double cw[NL][4];
+    int ii_prev = -1000;
+#pragma unroll 1
     for (int i = 0; i < p.nrows; i++) {
       const double t = ks * chi[i];
       int ii = (int)t;                       // t >= 0: truncation == floor
@@ -215,10 +222,24 @@ __global__ void __launch_bounds__(NT) project_kernel(ProjectParams p) {
       const double w3 = d2 * d * (1.0 / 6.0);
       const double vT = hasT ? __ldg(sT + (size_t)i * p.ld) : 0.0;
       const double vP = hasP ? __ldg(sP + (size_t)i * p.ld) : 0.0;
+      const int delta = ii_prev - ii;
+      if (delta != 0) {
+        const double* c = tabs + ii;
+        if (delta == 1) {
+#pragma unroll
+          for (int l = 0; l < NL; l++) { cw[l][3] = cw[l][2]; cw[l][2] = cw[l][1]; cw[l][1] = cw[l][0]; cw[l][0] = c[l * BESSEL_NC]; }
+        } else if (delta == 2) {
+#pragma unroll
+          for (int l = 0; l < NL; l++) { cw[l][3] = cw[l][1]; cw[l][2] = cw[l][0]; cw[l][1] = c[l * BESSEL_NC + 1]; cw[l][0] = c[l * BESSEL_NC]; }
+        } else {
+#pragma unroll
+          for (int l = 0; l < NL; l++) { cw[l][0] = c[l * BESSEL_NC]; cw[l][1] = c[l * BESSEL_NC + 1]; cw[l][2] = c[l * BESSEL_NC + 2]; cw[l][3] = c[l * BESSEL_NC + 3]; }
+        }
+        ii_prev = ii;
+      }
 #pragma unroll
       for (int l = 0; l < NL; l++) {
-        const double* c = tabs + l * BESSEL_NC + ii;
-        const double bes = c[0] * w0 + c[1] * w1 + c[2] * w2 + c[3] * w3;
+        const double bes = cw[l][0] * w0 + cw[l][1] * w1 + cw[l][2] * w2 + cw[l][3] * w3;
         th[l] += bes * vT;
         ep[l] += bes * vP;
       }
