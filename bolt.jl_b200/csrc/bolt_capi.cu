@@ -277,6 +277,7 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
                      const bolt_opts* o, double* d_ST, double* d_SP, double* d_hist, double* d_final, int* d_status,
                      long long* d_nsteps, long long* d_nreject, const DevCosmo* const* view_list = nullptr) {
   SolveParams p;
+  p.sync_mask = getenv("BOLT_K1_SYNCMASK") ? (int)strtol(getenv("BOLT_K1_SYNCMASK"), nullptr, 0) : 0x02;     // lockstep kernel: meet once per step (before stage 1)
   p.view_list = view_list;
   p.cos_list = cos_list; p.nk_per = nk_per; p.k = d_k; p.order = d_order; p.nk = nk;
   p.L = o->l_gamma; p.Lnu = o->l_nu; p.Lm = o->l_mnu;

@@ -50,6 +50,7 @@ struct SolveParams {
   double* dbg;            // optional step log of mode 0: [dbg_cap][4] = x, dt, EEst, accepted
   int dbg_cap;
   const DevCosmo* const* view_list;   // dual kernels, one cosmology: single-partial views [np] of the K1 cosmology (or null)
+  int sync_mask;          // lockstep kernel: bit s set = the warps of a block meet before stage s (1..6)
 };
 
 static __constant__ double c_rl[MAX_L + 1];   // l/(2l+1)
@@ -1072,8 +1073,9 @@ __host__ __device__ constexpr int k1_extra_doubles() { return TR::MAXLEN > 0 ? (
 #ifndef K1_MINBLOCKS
 #define K1_MINBLOCKS 8
 #endif
-// WPB > 1 (register-resident truncations only): WPB warps per block, each still owning its own k-mode, kept in LOCKSTEP at stage
-// granularity by one named barrier at the top of every stage.  The kernel is instruction-fetch bound when its warps roam
+// WPB > 1 (register-resident truncations only): WPB warps per block, each still owning its own k-mode, kept in loose LOCKSTEP by a
+// named barrier before the stages selected by p.sync_mask (default: once per step, before stage 1 -- measured as good as before
+// every stage, profiles/r2/k1_warp_lockstep_sweep.log, and cheaper in barrier waits).  The kernel is instruction-fetch bound when its warps roam
 // independently through the 61 KB step loop (ncu, profiles/r2/k1_warp_occupancy_sweep.md: stall_no_inst 2 % with one warp per
 // SM, 10 % with four, 18 % with eight): every stage executes the same 25 KB of code, so warps that enter it together share the
 // instruction-cache fills.  A warp that runs out of work keeps arriving at the barrier until every warp of the block has.
@@ -1202,7 +1204,7 @@ __global__ void __launch_bounds__(32 * WPB, (K1_MINBLOCKS / WPB > 0 ? K1_MINBLOC
         constexpr bool FLAT = (NCH == TR::NQ + 4);
         const bool live = (NCH == 32) || FLAT || ln.kind != CH_IDLE;
         for (int s = 1; s <= 6; s++) {
-          if constexpr (WPB > 1) asm volatile("bar.sync 1, %0;" ::"r"(32 * WPB) : "memory");      // lockstep (see the kernel's header)
+          if constexpr (WPB > 1) { if ((p.sync_mask >> s) & 1) asm volatile("bar.sync 1, %0;" ::"r"(32 * WPB) : "memory"); }     // lockstep (see the kernel's header)
           // z slot of this stage: Z1 and Z5 swap physical slots with the step parity, Z2..Z4 sit at slots 3..5
           double* zout = sm + (size_t)((s == 1) ? (flipU ? 0 : 2) : (s >= 5) ? (flipZ ? 1 : 6) : s + 1) * na;
           if (s <= 5) {
