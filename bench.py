@@ -498,10 +498,11 @@ def main():
         total_solves = NK * args.steps * world
         value = total_solves / wall_max
         fl = nstep_tot * f_step(n)        # accepted + rejected step attempts (bolt_spectra returns both counts)
-        roof = {"kernel": "hierarchy_kernel (K1, dominant)", "bound": "fp64", "achieved": fl / (k1_ms * 1e-3) / 1e12, "peak": fp64_peak,
+        roof = {"kernel": "hierarchy_kernel_t<Trunc<8,8,10,15,19>, 4> (K1, dominant: 73 % of the step)", "bound": "fp64", "achieved": fl / (k1_ms * 1e-3) / 1e12, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": fl / (k1_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                "traffic": None, "traffic_note": "not measured in this run; ncu --set full of this kernel (profiles/, see profiles/README.md for the capture's commit): "
-                                                 "~1 MB of DRAM traffic per launch -- K1 is not HBM bound",
+                "traffic": 4.5e5, "traffic_note": "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel "
+                                                  "on the same 2000-mode grid (profiles/r2/k1_warp_lockstep_2000modes.md, round 2): 295 KB + 156 KB per launch -- "
+                                                  "K1 never touches HBM in steady state",
                 "peak_source": "DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
                 "note": "algorithmic flop = step attempts (accepted + rejected) x (182 n + 3300), n = 197 (DESIGN.md); stall analysis in profiles/"}
         hbm_peak = None
@@ -513,7 +514,8 @@ def main():
         k2_bytes = (2 * 799 * 4999 * 8) + nell * 5003 * 8      # one read of the dense source grids + the spline tables
         k2_terms = 2.0 * nell * 4999 * 799
         roof_k2 = {"kernel": "project_kernel (K2)", "bound": "hbm", "achieved": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                   "unit": "GB/s", "frac": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                   "unit": "GB/s", "frac": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": 2.94e8,
+                   "traffic_note": "NOT measured in this run: one ncu --set full capture (profiles/r2/k2_projection.md): 288 MB read + 5.7 MB written per launch",
                    "fp64_tflops": 25.0 * k2_terms / 2 * args.steps / (k2_ms * 1e-3) / 1e12,
                    "note": "K2 is FP64/shared-memory-gather bound, not HBM bound (SURVEY 8d): both figures reported"}
         line = {"metric": "kmode_hierarchy_solves_per_s", "value": value, "unit": "k-mode solves/s", "n_gpus": world, "steps": args.steps,
