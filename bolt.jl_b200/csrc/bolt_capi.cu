@@ -25,9 +25,7 @@
 
 using namespace bolt;
 
-namespace bolt {      // k1_cta.cu: the warp-specialised K1 (one CTA per k-mode), its own translation unit
-int k1_cta_init_constants();
-cudaError_t k1_cta_launch(const SolveParams& p, int num_sms, cudaStream_t st, int* grid_out);
+namespace bolt {      // kernels with their own translation units (compiled in parallel)
 int k1_dual_cta_init_constants();  // k1_dual_cta.cu: K1 with partials, one CTA per mode (value warp + one warp per sensitivity system)
 cudaError_t k1_dual_cta_launch(const SolveParams& p, int np, int num_sms, cudaStream_t st);
 int k1_pipe_init_constants();      // k1_pipe.cu: the pipelined K1 (one CTA per k-mode, six warps by role)
@@ -156,7 +154,6 @@ int init_constants(bolt_ctx* ctx) {
   double rl1[MAX_L + 1];
   for (int l = 0; l <= MAX_L; l++) rl1[l] = 1.0 - rl[l];
   CUDA_OK(cudaMemcpyToSymbol(c_rl1, rl1, sizeof(rl1)));
-  if (k1_cta_init_constants()) return fail(ctx, BOLT_ERR_CUDA, "constant tables of k1_cta.cu");
   if (k1_pipe_init_constants()) return fail(ctx, BOLT_ERR_CUDA, "constant tables of k1_pipe.cu");
   if (k1_dual_cta_init_constants()) return fail(ctx, BOLT_ERR_CUDA, "constant tables of k1_dual_cta.cu");
   g_const_init[ctx->device] = true;
@@ -207,16 +204,6 @@ int launch_k1(bolt_ctx* ctx, const SolveParams& p) {
   CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
   kern<<<grid, 32, smem, ctx->stream>>>(p);
   CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  ctx->timing[4] += 1;
-  return BOLT_OK;
-}
-
-// One CTA per k-mode, warp-specialised (hierarchy_cta.cuh)
-int launch_k1_cta(bolt_ctx* ctx, const SolveParams& p) {
-  CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-  CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CUDA_OK(k1_cta_launch(p, ctx->num_sms, ctx->stream, nullptr));
   CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
   ctx->timing[4] += 1;
   return BOLT_OK;
@@ -324,9 +311,8 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
     // per-mode latency (one mode: 12.9 vs 33.1 ms; 296 modes: 15.4 vs 33.1 ms) but holds only 2 modes per SM; the one-warp-per-mode
     // kernel holds 8 and wins once the modes outnumber the resident CTAs several times (500 modes: 16.0 vs 34.1 ms, 1000: 30.5 vs 42.3,
     // 1400: 41.5 vs 44.4, 2000: 59.6 vs 46.8 ms).
-    // BOLT_K1_PIPE=1 / BOLT_K1_WARP=1 / BOLT_K1_CTA=1 (the first CTA kernel, kept for comparison) force one.
+    // BOLT_K1_PIPE=1 / BOLT_K1_WARP=1 force one.
     if (p.L == 8 || p.L == 10) {
-      if (getenv("BOLT_K1_CTA")) return launch_k1_cta(ctx, p);
       if (getenv("BOLT_K1_PIPE") || (!getenv("BOLT_K1_WARP") && p.nk <= 9 * ctx->num_sms)) return launch_k1_pipe(ctx, p);
     }
     // Beyond that the one-warp-per-mode kernel, four warps per block in lockstep at stage granularity (shared instruction-cache

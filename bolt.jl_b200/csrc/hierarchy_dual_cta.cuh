@@ -18,7 +18,7 @@
 // functions in dual arithmetic are the very functions of hierarchy_dual.cuh (run by warp 0 on the full Dual<NP> view).
 #pragma once
 #include "hierarchy_dual_reg.cuh"
-#include "hierarchy_cta.cuh"
+#include "stage_slot.cuh"
 
 namespace bolt {
 

@@ -705,7 +705,7 @@ __device__ __forceinline__ void ge4(const double (&Min)[4][4], const double (&rh
 template <bool CB> __device__ __forceinline__ double rl_of(int l) { return CB ? c_rl[l] : RLc(l); }
 template <bool CB> __device__ __forceinline__ double rl1_of(int l) { return CB ? c_rl1[l] : 1.0 - RLc(l); }
 
-template <class TR, bool CB = true, class FT>      // FT: RegFactor<TR> (lane-private scratch) or SlotFactor<TR> (hierarchy_cta.cuh)
+template <class TR, bool CB = true, class FT>      // FT: RegFactor<TR> (lane-private scratch) or SlotFactor<TR> (stage_slot.cuh)
 __device__ __forceinline__ void factor_reg(const Lane& ln, const BgS& b, double h, FT& f) {
   constexpr int MAXLEN = TR::MAXLEN;
   const int kind = ln.kind;

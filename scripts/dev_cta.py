@@ -1,4 +1,4 @@
-"""Development check (GPU): the CTA-per-mode K1 kernels (pipe: hierarchy_pipe.cuh, cta: hierarchy_cta.cuh) against the one-warp kernel: parity + timing."""
+"""Development check (GPU): the pipelined CTA-per-mode K1 kernel (DEV_NEW=pipe, hierarchy_pipe.cuh; DEV_NEW=auto: the library's dispatch) against the one-warp kernel: parity + timing."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

@@ -1,4 +1,5 @@
-"""Development (GPU): cycle counters of the CTA-per-mode K1 roles (library built with -DK1C_PROF, BOLT_CUDA_LIB=...)."""
+"""Development (GPU): cycle counters of the pipelined K1 kernel's solver warp (k1_pipe.cu built with -DK1P_PROF into a library
+selected by BOLT_CUDA_LIB, BOLT_K1_PIPE=1).  The rows of the first CTA kernel (removed) are kept for reading old logs."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["BOLT_DEBUG_STEPS"] = "/tmp/k1c_prof.txt"

@@ -1,4 +1,4 @@
-"""Development (GPU): one K1 launch of the selected kernel (BOLT_K1_PIPE / BOLT_K1_WARP / BOLT_K1_CTA) for ncu captures."""
+"""Development (GPU): one K1 launch of the selected kernel (BOLT_K1_PIPE / BOLT_K1_WARP; default: the library's dispatch) for ncu captures."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
