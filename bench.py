@@ -203,6 +203,29 @@ def plin_arm(ctx, hcosmo, dc):
             "hierarchy_ms": ctx.timing()["hierarchy_ms"], "ode_steps_per_solve": float(ns.mean()), "failed_modes": int((st != 0).sum())}
 
 
+def params_to_spectra_arm(ctx, local_rank, ells, ncos=16):
+    """BASELINE configs[4] in miniature, end to end ON THE DEVICE: parameter sets in, TT/TE/EE out -- input tables by
+    bolt_hostgen_batch (one call for the batch), upload, bolt_spectra per cosmology.  What an emulator / MCMC driver would run."""
+    import bolt_b200 as B
+    from bolt_b200 import abi, capi
+    pars = [synthetic_params(100 + i) for i in range(ncos)]
+    o = abi.make_opts(LG, 8, 10, reltol=RELTOL, abstol=ABSTOL)
+    t0 = time.perf_counter()
+    hcs, st = capi.hostgen_batch(pars, device=local_rank)
+    t_gen = time.perf_counter() - t0
+    bad = 0
+    for hc in hcs:
+        H0 = hc.scalar("H0")
+        dc = capi.DeviceCosmo(ctx, hc)
+        k = B.quadratic_k(0.1 * H0, 1000 * H0, NK)
+        out = dc.spectra(k, o, ells, 0.01 * H0, 1000 * H0, 5000, 1201)
+        bad += int((out[3] != 0).sum()); dc.close()
+    dt = time.perf_counter() - t0
+    return {"workload": f"{ncos} parameter sets -> input tables on the device (one bolt_hostgen_batch call) -> upload -> C3-value spectra per cosmology",
+            "ms_per_cosmology": 1e3 * dt / ncos, "spectra_per_s": ncos / dt, "table_generation_ms_per_call": 1e3 * t_gen,
+            "failed_modes": bad, "failed_tables": int((st != 0).sum())}
+
+
 def hostgen_arm(local_rank, ncos=256):
     """the input tables (background, RECFAST, reionization, optical depth and their spline coefficients) of a BATCH of
     synthetic cosmologies on the device (bolt_hostgen_batch: one thread integrates the recombination ODEs of one cosmology), beside
@@ -547,6 +570,7 @@ def main():
             line["plin"] = guarded(plin_arm, ctx, hcos[0], dcs[0])
             line["batch"] = guarded(batch_arm, ctx, hcos, dcs, ells)
             line["hostgen"] = guarded(hostgen_arm, local_rank)
+            line["params_to_spectra"] = guarded(params_to_spectra_arm, ctx, local_rank, ells)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
