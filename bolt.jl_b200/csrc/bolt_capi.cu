@@ -329,7 +329,14 @@ int launch_hierarchy(bolt_ctx* ctx, const DevCosmo* const* cos_list, int nq, int
     if (p.L == 10) return launch_k1<Trunc<10, 8, 10, 15, K1_NCH>>(ctx, p);       // l_gamma = 10: BASELINE config 1
   }
   // any other truncation (plin: 50/50/20, C4: 50/8/10): the runtime-truncation path needs l_max >= 2 on every chain
-  if (!force_generic && p.L >= 2 && p.Lnu >= 2 && p.Lm >= 2) return launch_k1<TruncRT>(ctx, p);
+  if (!force_generic && p.L >= 2 && p.Lnu >= 2 && p.Lm >= 2) {
+    if (getenv("BOLT_K1_RT_WPB")) {      // development: lockstep blocks for the runtime-truncation path
+      const int wpb = atoi(getenv("BOLT_K1_RT_WPB"));
+      if (wpb == 2) return launch_k1_lockstep<TruncRT, 2>(ctx, p);
+      if (wpb == 4) return launch_k1_lockstep<TruncRT, 4>(ctx, p);
+    }
+    return launch_k1<TruncRT>(ctx, p);
+  }
   return launch_k1<Trunc<0, 0, 0, 0>>(ctx, p);
 }
 int launch_hierarchy(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, const int* d_order, int nk, const bolt_opts* o,

@@ -1317,6 +1317,7 @@ __global__ void __launch_bounds__(32 * WPB, (K1_MINBLOCKS / WPB > 0 ? K1_MINBLOC
         double r5[5], q5[5], r0, r1, r2;
         const int iS = ln.iS;
         for (int s = 1; s <= 6; s++) {
+          if constexpr (WPB > 1) { if ((p.sync_mask >> s) & 1) asm volatile("bar.sync 1, %0;" ::"r"(32 * WPB) : "memory"); }     // lockstep
           double* zout = (s == 1) ? Z1 : (s == 2) ? Z2 : (s == 3) ? Z3 : (s == 4) ? Z4 : Z5;
           if (s <= 5) {
             const double a0 = KC_A[s][0] * s1, a1 = KC_A[s][1], a2 = KC_A[s][2], a3 = KC_A[s][3], a4 = KC_A[s][4];
