@@ -246,6 +246,42 @@ def hostgen_arm(local_rank, ncos=256):
             "speedup_vs_cpu_baseline": (ncos / dt) * t_cpu}
 
 
+def filon_arm(local_rank, n_k=2000, n_nodes=2048, cpu_k=2000):
+    """the reference's Bessel-moment table (src/bessel/interpolator.jl:67-110: 2,000,000 nodes on kη in (0, 1.6e4),
+    ν = 2) built on the device, then a line-of-sight-shaped Filon workload: for each of n_k wavenumbers, the chain of quadratic
+    source pieces between n_nodes conformal-distance nodes (integrator.jl:25-38).  CPU arm: the numpy-vectorised oracle doing
+    the same gathers from a table it built itself (one core)."""
+    import bolt_b200.bessel as BM
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bessel_moments_oracle as BO
+    N, XMAX = 2_000_000, 1.6e4
+    BM.sph_bessel_interpolator(2, 3, 0.0, 100.0, 1000).close()                  # load + first-launch cost out of the way
+    t0 = time.perf_counter(); itp = BM.sph_bessel_interpolator(2, 3, 0.0, XMAX, N, device=local_rank); t_build = time.perf_counter() - t0
+    nodes = np.linspace(0.0, 14000.0, n_nodes)
+    k = np.linspace(1e-4, 1.0, n_k)
+    g = np.exp(-0.5 * ((nodes - 13800.0) / 60.0) ** 2)[None, :] * np.cos(k[:, None] * 0.3)
+    d1 = -(nodes - 13800.0)[None, :] / 3600.0 * g
+    d2 = (((nodes - 13800.0) ** 2 / 3600.0 - 1.0) / 3600.0)[None, :] * g
+    out, ms = BM.filon_chain(nodes, g, d1, d2, k, itp, timing=True)
+    t0 = time.perf_counter(); out, ms = BM.filon_chain(nodes, g, d1, d2, k, itp, timing=True); t_call = time.perf_counter() - t0
+    itp.close()
+    t0 = time.perf_counter(); ora = BO.MomentTable(2, 3, 0.0, XMAX, N); t_build_cpu = time.perf_counter() - t0
+    sel = np.linspace(0, n_k - 1, cpu_k).astype(int)
+    t0 = time.perf_counter(); ref = BO.filon_chain(nodes, g[sel], d1[sel], d2[sel], k[sel], ora); t_cpu = time.perf_counter() - t0
+    # the chain sums cancel heavily (oscillatory integrand; the rule's c0, c1, c2 are powers of x, not of x - a): compare on the
+    # scale of the largest chain
+    err = float(np.max(np.abs(out[sel] - ref)) / np.abs(ref).max())
+    pieces = n_k * (n_nodes - 1)
+    return {"workload": f"moment table ν=2, order 3, {N} nodes on (0, {XMAX:g}); Filon chains: {n_k} wavenumbers x {n_nodes - 1} quadratic pieces",
+            "table_build_ms": 1e3 * t_build, "chain_kernel_ms": ms, "chain_call_ms_host_buffers": 1e3 * t_call,
+            "pieces_per_s_kernel": pieces / (1e-3 * ms), "table_gather_GBps": pieces * 96 / (1e-3 * ms) / 1e9,
+            "max_diff_vs_oracle_over_largest_chain": err,
+            "cpu_baseline": {"table_build_s": t_build_cpu, "value": cpu_k * (n_nodes - 1) / t_cpu, "unit": "pieces/s", "cores": 1, "kind": "port",
+                             "sample": f"{cpu_k} of the {n_k} wavenumbers through oracle/bessel_moments_oracle.py (numpy, {t_cpu:.2f} s); "
+                                       f"its table build took {t_build_cpu:.1f} s (40-digit sums for the 6250 nodes below kη = 50)"},
+            "speedup_vs_cpu_baseline_kernel": (pieces / (1e-3 * ms)) / (cpu_k * (n_nodes - 1) / t_cpu)}
+
+
 def batch_arm(ctx, hcos, dcs, ells, ncos=4):
     """SURVEY 8d C5 (emulator / MCMC batches): the same C3-value workload through bolt_spectra_batch, ncos cosmologies per call --
     all ncos x 2000 hierarchy solves in ONE launch, so the tail of the persistent kernel is paid once per batch."""
@@ -571,6 +607,7 @@ def main():
             line["batch"] = guarded(batch_arm, ctx, hcos, dcs, ells)
             line["hostgen"] = guarded(hostgen_arm, local_rank)
             line["params_to_spectra"] = guarded(params_to_spectra_arm, ctx, local_rank, ells)
+            line["filon"] = guarded(filon_arm, local_rank)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

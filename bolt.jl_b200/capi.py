@@ -17,7 +17,9 @@ EXPORTS = ["bolt_abi_version", "bolt_init", "bolt_finalize", "bolt_last_error", 
            "bolt_cosmo_upload", "bolt_cosmo_free", "bolt_state_dim", "bolt_solve", "bolt_project",
            "bolt_spectra", "bolt_spectra_batch", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak", "bolt_set_bessel_xmax",
            "bolt_comm_unique_id", "bolt_comm_init", "bolt_comm_free", "bolt_spectra_sharded", "bolt_shard_plan", "bolt_fftlog",
-           "bolt_hostgen_batch", "bolt_hostgen_last_error"]
+           "bolt_hostgen_batch", "bolt_hostgen_last_error",
+           "bolt_sph_j_moments", "bolt_moment_table_create", "bolt_moment_table_free", "bolt_moment_table_eval",
+           "bolt_filon_pieces", "bolt_filon_chain", "bolt_moments_last_error"]
 
 
 class BoltError(RuntimeError):
@@ -60,6 +62,13 @@ def lib():
         L.bolt_hostgen_batch.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, C.c_int, dp, dp, ip]
         L.bolt_hostgen_last_error.restype = C.c_char_p
         L.bolt_fftlog.argtypes = [vp, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, dp, dp, dp]
+        L.bolt_sph_j_moments.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, dp]
+        L.bolt_moment_table_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.POINTER(vp)]
+        L.bolt_moment_table_free.argtypes = [vp]; L.bolt_moment_table_free.restype = None
+        L.bolt_moment_table_eval.argtypes = [vp, dp, C.c_int, dp]
+        L.bolt_filon_pieces.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, dp]
+        L.bolt_filon_chain.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_float)]
+        L.bolt_moments_last_error.restype = C.c_char_p
         _LIB = L
     return _LIB
 

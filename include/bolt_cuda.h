@@ -200,6 +200,35 @@ int  bolt_hostgen_batch(int device_ordinal, const double* params, int ncos, doub
                         double* tables_out, double* scalars_out, int32_t* status_out);
 const char* bolt_hostgen_last_error(void);
 
+/* Bessel-moment tables and the Filon line-of-sight rule.  Replaces, on the device,
+ *   src/bessel/moments.jl:56-112      sph_j_moment_{weniger_1F2, asymp, maclaurin_1F2} (and, through J_nu = sqrt(2t/pi) j_{nu-1/2},
+ *                                     the J_moment_* building blocks of moments.jl:24-51: pass half-integer powers)
+ *   src/bessel/interpolator.jl:26-110 sph_bessel_interpolator(nu, order, keta_min, keta_max, N; weniger_cut) and the MomentTable call
+ *   src/bessel/integrator.jl:7-38     integrate_sph_bessel_filon and its loop form.
+ * All pointers are HOST buffers.  No context: calls select `device_ordinal` themselves (a table remembers its device).
+ *   bolt_sph_j_moments   out[n][n_powers] = int_0^x t^power j_nu(t) dt at x[n]; powers NULL means 0,1,..,n_powers-1 (n_powers <= 4);
+ *                        method 0: the small-argument evaluator (the role of the reference's Double64 Weniger sum; here Maclaurin
+ *                        below x = 4, Gauss-Legendre pieces on a double-double prefix table above), 1: Lommel asymptotic form,
+ *                        2: Maclaurin series.  nu = 1, 2, 3.
+ *   bolt_moment_table_create  the N-node cubic-B-spline table of the first `order` (3 or 4; 1..4 accepted) moments on
+ *                        [keta_min, keta_max], nu = 2 or 3; nodes below weniger_cut from method 0, above from method 1.
+ *   bolt_moment_table_eval    out[n][order]: the table inside its range, Maclaurin below, asymptotic above (interpolator.jl:26-34).
+ *   bolt_filon_pieces    out[i] = int_a^b (f + f'(x-a) + f''(x-a)^2/2) j_nu(k x) dx for n independent pieces (order >= 3).
+ *   bolt_filon_chain     for every k[n_k]: the sum of the pieces between consecutive nodes[n_nodes] with f, f', f'' given at the
+ *                        nodes as [n_k][n_nodes]; each node's moments are evaluated once (the loop form, integrator.jl:25-38).
+ *                        kernel_ms (may be NULL): device time of one warm launch. */
+typedef struct bolt_moment_table bolt_moment_table;
+int  bolt_sph_j_moments(int device_ordinal, int nu, int n_powers, const double* powers, int method, const double* x, int n, double* out);
+int  bolt_moment_table_create(int device_ordinal, int nu, int order, double keta_min, double keta_max, int N, double weniger_cut,
+                              bolt_moment_table** out);
+void bolt_moment_table_free(bolt_moment_table* t);
+int  bolt_moment_table_eval(bolt_moment_table* t, const double* x, int n, double* out);
+int  bolt_filon_pieces(bolt_moment_table* t, int n, const double* f, const double* f1, const double* f2, const double* k,
+                       const double* a, const double* b, double* out);
+int  bolt_filon_chain(bolt_moment_table* t, int n_k, int n_nodes, const double* nodes, const double* f, const double* f1,
+                      const double* f2, const double* k, double* out, float* kernel_ms);
+const char* bolt_moments_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif
