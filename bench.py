@@ -246,14 +246,20 @@ def hostgen_arm(local_rank, ncos=256):
             "speedup_vs_cpu_baseline": (ncos / dt) * t_cpu}
 
 
+def cpu_filon_chain(nodes, f, f1, f2, k, N, xmax):
+    """CPU leg of filon_arm: the oracle builds its own ν = 2 moment table and runs the same chains (numpy, one core)."""
+    from oracle import bessel_moments_oracle as BO
+    t0 = time.perf_counter(); ora = BO.MomentTable(2, 3, 0.0, xmax, N); t_build = time.perf_counter() - t0
+    t0 = time.perf_counter(); ref = BO.filon_chain(nodes, f, f1, f2, k, ora); t_run = time.perf_counter() - t0
+    return ref, t_build, t_run
+
+
 def filon_arm(local_rank, n_k=2000, n_nodes=2048, cpu_k=2000):
     """the reference's Bessel-moment table (src/bessel/interpolator.jl:67-110: 2,000,000 nodes on kη in (0, 1.6e4),
     ν = 2) built on the device, then a line-of-sight-shaped Filon workload: for each of n_k wavenumbers, the chain of quadratic
     source pieces between n_nodes conformal-distance nodes (integrator.jl:25-38).  CPU arm: the numpy-vectorised oracle doing
     the same gathers from a table it built itself (one core)."""
     import bolt_b200.bessel as BM
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import bessel_moments_oracle as BO
     N, XMAX = 2_000_000, 1.6e4
     BM.sph_bessel_interpolator(2, 3, 0.0, 100.0, 1000).close()                  # load + first-launch cost out of the way
     t0 = time.perf_counter(); itp = BM.sph_bessel_interpolator(2, 3, 0.0, XMAX, N, device=local_rank); t_build = time.perf_counter() - t0
@@ -265,16 +271,15 @@ def filon_arm(local_rank, n_k=2000, n_nodes=2048, cpu_k=2000):
     out, ms = BM.filon_chain(nodes, g, d1, d2, k, itp, timing=True)
     t0 = time.perf_counter(); out, ms = BM.filon_chain(nodes, g, d1, d2, k, itp, timing=True); t_call = time.perf_counter() - t0
     itp.close()
-    t0 = time.perf_counter(); ora = BO.MomentTable(2, 3, 0.0, XMAX, N); t_build_cpu = time.perf_counter() - t0
     sel = np.linspace(0, n_k - 1, cpu_k).astype(int)
-    t0 = time.perf_counter(); ref = BO.filon_chain(nodes, g[sel], d1[sel], d2[sel], k[sel], ora); t_cpu = time.perf_counter() - t0
+    ref, t_build_cpu, t_cpu = cpu_filon_chain(nodes, g[sel], d1[sel], d2[sel], k[sel], N, XMAX)
     # the chain sums cancel heavily (oscillatory integrand; the rule's c0, c1, c2 are powers of x, not of x - a): compare on the
     # scale of the largest chain
     err = float(np.max(np.abs(out[sel] - ref)) / np.abs(ref).max())
     pieces = n_k * (n_nodes - 1)
     return {"workload": f"moment table ν=2, order 3, {N} nodes on (0, {XMAX:g}); Filon chains: {n_k} wavenumbers x {n_nodes - 1} quadratic pieces",
             "table_build_ms": 1e3 * t_build, "chain_kernel_ms": ms, "chain_call_ms_host_buffers": 1e3 * t_call,
-            "pieces_per_s_kernel": pieces / (1e-3 * ms), "table_gather_GBps": pieces * 96 / (1e-3 * ms) / 1e9,
+            "pieces_per_s_kernel": pieces / (1e-3 * ms), "table_gather_GBps": pieces * 128 / (1e-3 * ms) / 1e9,
             "max_diff_vs_oracle_over_largest_chain": err,
             "cpu_baseline": {"table_build_s": t_build_cpu, "value": cpu_k * (n_nodes - 1) / t_cpu, "unit": "pieces/s", "cores": 1, "kind": "port",
                              "sample": f"{cpu_k} of the {n_k} wavenumbers through oracle/bessel_moments_oracle.py (numpy, {t_cpu:.2f} s); "

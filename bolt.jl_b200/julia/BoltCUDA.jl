@@ -364,4 +364,90 @@ function fftlog(r::AbstractVector, a::AbstractVector, μ, q, k₀r₀=1.0; kropt
     complex.(y[1, :], y[2, :]), k
 end
 
+# ---- batched input tables (src/background.jl:104-128, src/ionization/recfast.jl:446-536,674-726), SURVEY 8f row n1 ------------------
+"""`hostgen_batch(pars)`: the 12 spline-coefficient tables and 13 scalars of every cosmology in `pars` computed on the device in
+one call (what `Background` + `RECFAST` + `IonizationHistory` compute on the host one at a time).  Returns
+(tables[n_x+2, 12, ncos], scalars[13, ncos], status[ncos]) in the layout `bolt_cosmo_upload` reads (nd = 1)."""
+function hostgen_batch(pars::AbstractVector{<:AbstractCosmoParams}; x0=-20.0, dx=0.01, n_x=2001, nq=15, dev=Device())
+    ncos = length(pars)
+    P = zeros(Float64, 9, ncos)
+    for (i, 𝕡) in enumerate(pars)
+        P[:, i] .= (𝕡.h, 𝕡.Ω_r, 𝕡.Ω_b, 𝕡.Ω_c, 𝕡.A, 𝕡.n, 𝕡.Y_p, 𝕡.N_ν, 𝕡.Σm_ν)
+    end
+    pts, wts = Bolt.gausslegendre(nq)
+    pts = Float64.(pts); wts = Float64.(wts)
+    tabs = zeros(Float64, n_x + 2, 12, ncos); sc = zeros(Float64, 13, ncos); st = zeros(Int32, ncos)
+    rc = GC.@preserve P pts wts tabs sc st ccall((:bolt_hostgen_batch, lib), Cint,
+        (Cint, Ptr{Float64}, Cint, Cdouble, Cdouble, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+        dev.ordinal, P, ncos, x0, dx, n_x, pts, wts, nq, tabs, sc, st)
+    rc == 0 || error("bolt_hostgen_batch: " * unsafe_string(ccall((:bolt_hostgen_last_error, lib), Cstring, ())))
+    tabs, sc, st
+end
+
+# ---- Bessel-moment tables and the Filon rule (src/bessel/*.jl), SURVEY 8f row n2 ------------------------------------------------
+moments_check(rc, what) = rc == 0 || error(what * ": " * unsafe_string(ccall((:bolt_moments_last_error, lib), Cstring, ())))
+
+"""Device counterpart of `Bolt.MomentTable` (src/bessel/interpolator.jl:19-38): callable, returns the `order` moments at x."""
+mutable struct DeviceMomentTable
+    handle::Ptr{Cvoid}
+    ν::Int
+    order::Int
+    kη_min::Float64
+    kη_max::Float64
+end
+Bolt.getnu(t::DeviceMomentTable) = t.ν
+Bolt.getorder(t::DeviceMomentTable) = t.order
+
+"""`sph_bessel_interpolator(dev, ν, order, kη_min, kη_max, N; weniger_cut=50)` (src/bessel/interpolator.jl:67-80)."""
+function Bolt.sph_bessel_interpolator(dev::Device, ν::Int, order, kη_min, kη_max, N::Int; weniger_cut=50)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    moments_check(ccall((:bolt_moment_table_create, lib), Cint, (Cint, Cint, Cint, Cdouble, Cdouble, Cint, Cdouble, Ref{Ptr{Cvoid}}),
+        dev.ordinal, ν, order, kη_min, kη_max, N, weniger_cut, h), "bolt_moment_table_create")
+    t = DeviceMomentTable(h[], ν, order, kη_min, kη_max)
+    finalizer(x -> ccall((:bolt_moment_table_free, lib), Cvoid, (Ptr{Cvoid},), x.handle), t)
+    t
+end
+
+function (t::DeviceMomentTable)(x::AbstractVector)
+    xx = Float64.(x); out = zeros(Float64, t.order, length(xx))
+    GC.@preserve xx out moments_check(ccall((:bolt_moment_table_eval, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}),
+        t.handle, xx, length(xx), out), "bolt_moment_table_eval")
+    out
+end
+(t::DeviceMomentTable)(x::Real) = t([x])[:, 1]
+
+"""Direct moments ∫₀ˣ t^p j_ν(t) dt on the device: method 0 small-argument evaluator (the role of `sph_j_moment_weniger_₁F₂`),
+1 Lommel asymptotic form (`sph_j_moment_asymp`), 2 Maclaurin series (`sph_j_moment_maclaurin_₁F₂`); src/bessel/moments.jl:56-83."""
+function sph_j_moments(x::AbstractVector, ν::Int, powers::AbstractVector; method=0, dev=Device())
+    xx = Float64.(x); pp = Float64.(powers); out = zeros(Float64, length(pp), length(xx))
+    GC.@preserve xx pp out moments_check(ccall((:bolt_sph_j_moments, lib), Cint,
+        (Cint, Cint, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64}),
+        dev.ordinal, ν, length(pp), pp, method, xx, length(xx), out), "bolt_sph_j_moments")
+    out
+end
+
+"""`integrate_sph_bessel_filon(f, f′, f″, k, a, b, itp)` for vectors of independent pieces (src/bessel/integrator.jl:7-20)."""
+function Bolt.integrate_sph_bessel_filon(f::AbstractVector, f′::AbstractVector, f″::AbstractVector, k::AbstractVector,
+                                         a::AbstractVector, b::AbstractVector, itp::DeviceMomentTable)
+    n = length(f); v = map(x -> Float64.(x), (f, f′, f″, k, a, b)); out = zeros(Float64, n)
+    GC.@preserve v out moments_check(ccall((:bolt_filon_pieces, lib), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        itp.handle, n, v[1], v[2], v[3], v[4], v[5], v[6], out), "bolt_filon_pieces")
+    out
+end
+Bolt.integrate_sph_bessel_filon(f::Real, f′::Real, f″::Real, k::Real, a::Real, b::Real, itp::DeviceMomentTable) =
+    Bolt.integrate_sph_bessel_filon([f], [f′], [f″], [k], [a], [b], itp)[1]
+
+"""The loop form (src/bessel/integrator.jl:25-38) batched: for every k the sum of the pieces between consecutive `nodes`, with the
+quadratic's f, f′, f″ given at the nodes as (n_nodes, n_k) matrices.  One device block per k; each node's moments are evaluated once."""
+function filon_chain(nodes::AbstractVector, f::AbstractMatrix, f′::AbstractMatrix, f″::AbstractMatrix, k::AbstractVector, itp::DeviceMomentTable)
+    nn = length(nodes); nk = length(k)
+    size(f) == (nn, nk) || error("f must be (n_nodes, n_k)")
+    xs = Float64.(nodes); kk = Float64.(k); F = Float64.(f); F1 = Float64.(f′); F2 = Float64.(f″); out = zeros(Float64, nk)
+    GC.@preserve xs kk F F1 F2 out moments_check(ccall((:bolt_filon_chain, lib), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cfloat}),
+        itp.handle, nk, nn, xs, F, F1, F2, kk, out, C_NULL), "bolt_filon_chain")
+    out
+end
+
 end # module

@@ -7,8 +7,7 @@ import mpmath
 import numpy as np
 import pytest
 
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
-import bessel_moments_oracle as O  # noqa: E402
+from oracle import bessel_moments_oracle as O  # noqa: E402
 
 TOL = 1e-13          # test/testbessel.jl:4
 big = mpmath.mpf

@@ -8,8 +8,7 @@ import mpmath
 import numpy as np
 import pytest
 
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
-import bessel_moments_oracle as O  # noqa: E402
+from oracle import bessel_moments_oracle as O  # noqa: E402
 from test_bessel_moments import (J_MODERATE, MAC_001, MAC_0001, OCT_200, QUAD_200, REFS_4TH_1, REFS_4TH_1000, TOL, big, rel)  # noqa: E402
 
 pytestmark = pytest.mark.gpu

@@ -19,8 +19,9 @@ C2J = {
     "const double*": {"Ptr{Float64}"}, "double*": {"Ptr{Float64}"},
     "const int32_t*": {"Ptr{Int32}"}, "int32_t*": {"Ptr{Int32}"}, "int64_t*": {"Ptr{Int64}"},
     "void*": {"Ptr{Cvoid}"}, "const void*": {"Ptr{Cvoid}"},
+    "bolt_moment_table*": {"Ptr{Cvoid}"}, "bolt_moment_table**": {"Ref{Ptr{Cvoid}}"}, "float*": {"Ptr{Cfloat}"},
 }
-RET = {"int": "Cint", "const char*": "Cstring"}
+RET = {"int": "Cint", "const char*": "Cstring", "void": "Cvoid"}
 
 
 def split_top(s):
@@ -42,7 +43,7 @@ def split_top(s):
 def c_prototypes():
     src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
     protos = {}
-    for ret, name, args in re.findall(r"\b(int|const char\*)\s+(bolt_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    for ret, name, args in re.findall(r"\b(int|void|const char\*)\s+(bolt_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         params = []
         for a in split_top(" ".join(args.split())):
             if a == "void":
@@ -125,5 +126,8 @@ def test_shim_adds_methods_for_the_reference_signatures():
                 r"source_grid\(𝕡::AbstractCosmoParams, bg, ih, k_grid, dev::Device", r"source_grid_P\(𝕡::AbstractCosmoParams, bg, ih, k_grid, dev::Device",
                 r"cltt\(ℓ::Int, 𝕡::AbstractCosmoParams, bg, ih, sf::DeviceSourceGrid\)", r"clte\(ℓ::Int,", r"clee\(ℓ::Int,",
                 r"cltt\(ℓ⃗::AbstractVector,", r"cltt\(ℓ, s::DeviceSourceGrid, kgrid,", r"clte\(ℓ, s::DeviceSourceGrid, sP::DeviceSourceGrid, kgrid,",
-                r"clee\(ℓ, sP::DeviceSourceGrid, kgrid,", r"function plin\(ks::AbstractVector,", r"plin\(k::Real, 𝕡::AbstractCosmoParams, bg, ih, dev::Device"):
+                r"clee\(ℓ, sP::DeviceSourceGrid, kgrid,", r"function plin\(ks::AbstractVector,", r"plin\(k::Real, 𝕡::AbstractCosmoParams, bg, ih, dev::Device",
+                r"function Bolt.sph_bessel_interpolator\(dev::Device, ν::Int, order, kη_min, kη_max, N::Int; weniger_cut=50\)",
+                r"function Bolt.integrate_sph_bessel_filon\(f::AbstractVector,", r"Bolt.integrate_sph_bessel_filon\(f::Real,",
+                r"Bolt.getnu\(t::DeviceMomentTable\)", r"Bolt.getorder\(t::DeviceMomentTable\)", r"function hostgen_batch\(pars::AbstractVector"):
         assert re.search(pat, src), pat
