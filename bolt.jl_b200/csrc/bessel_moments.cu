@@ -480,11 +480,12 @@ extern "C" {
 const char* bolt_moments_last_error(void) { return g_bm_err.c_str(); }
 
 int bolt_sph_j_moments(int device_ordinal, int nu, int n_powers, const double* powers, int method, const double* x, int n, double* out) {
-  if (!x || !out || n < 0 || method < 0 || method > 2) { g_bm_err = "bad argument"; return BOLT_ERR_ARG; }
+  if (n < 0 || method < 0 || method > 2) { g_bm_err = "bad argument"; return BOLT_ERR_ARG; }
   MomentSpec sp;
   int rc = make_spec(nu, n_powers, powers, sp);
   if (rc != BOLT_OK) return rc;
   if (n == 0) return BOLT_OK;
+  if (!x || !out) { g_bm_err = "null buffer"; return BOLT_ERR_ARG; }
   BM_CHECK(cudaSetDevice(device_ordinal));
   double xtop = 0.0;
   for (int i = 0; i < n; i++) {
@@ -555,8 +556,9 @@ void bolt_moment_table_free(bolt_moment_table* t) {
 }
 
 int bolt_moment_table_eval(bolt_moment_table* t, const double* x, int n, double* out) {
-  if (!t || !x || !out || n < 0) { g_bm_err = "bad argument"; return BOLT_ERR_ARG; }
+  if (!t || n < 0) { g_bm_err = "bad argument"; return BOLT_ERR_ARG; }
   if (n == 0) return BOLT_OK;
+  if (!x || !out) { g_bm_err = "null buffer"; return BOLT_ERR_ARG; }
   for (int i = 0; i < n; i++) if (!(x[i] >= 0.0) || !std::isfinite(x[i])) { g_bm_err = "x must be finite and >= 0"; return BOLT_ERR_ARG; }
   BM_CHECK(cudaSetDevice(t->device));
   DevBuf dx, dout;
@@ -572,9 +574,10 @@ int bolt_moment_table_eval(bolt_moment_table* t, const double* x, int n, double*
 
 int bolt_filon_pieces(bolt_moment_table* t, int n, const double* f, const double* f1, const double* f2, const double* k, const double* a,
                       const double* b, double* out) {
-  if (!t || !f || !f1 || !f2 || !k || !a || !b || !out || n < 0) { g_bm_err = "bad argument"; return BOLT_ERR_ARG; }
+  if (!t || n < 0) { g_bm_err = "bad argument"; return BOLT_ERR_ARG; }
   if (t->order < 3) { g_bm_err = "the Filon rule needs a table of order >= 3 (quadratic pieces)"; return BOLT_ERR_ARG; }
   if (n == 0) return BOLT_OK;
+  if (!f || !f1 || !f2 || !k || !a || !b || !out) { g_bm_err = "null buffer"; return BOLT_ERR_ARG; }
   for (int i = 0; i < n; i++)
     if (!(k[i] > 0.0) || !(a[i] >= 0.0) || !(b[i] >= 0.0)) { g_bm_err = "need k > 0 and a, b >= 0"; return BOLT_ERR_ARG; }
   BM_CHECK(cudaSetDevice(t->device));
@@ -593,9 +596,10 @@ int bolt_filon_pieces(bolt_moment_table* t, int n, const double* f, const double
 
 int bolt_filon_chain(bolt_moment_table* t, int n_k, int n_nodes, const double* nodes, const double* f, const double* f1, const double* f2,
                      const double* k, double* out, float* kernel_ms) {
-  if (!t || !nodes || !f || !f1 || !f2 || !k || !out || n_k < 0 || n_nodes < 2) { g_bm_err = "bad argument"; return BOLT_ERR_ARG; }
+  if (!t || n_k < 0 || n_nodes < 2) { g_bm_err = "bad argument"; return BOLT_ERR_ARG; }
   if (t->order < 3) { g_bm_err = "the Filon rule needs a table of order >= 3 (quadratic pieces)"; return BOLT_ERR_ARG; }
   if (n_k == 0) return BOLT_OK;
+  if (!nodes || !f || !f1 || !f2 || !k || !out) { g_bm_err = "null buffer"; return BOLT_ERR_ARG; }
   for (int i = 0; i < n_nodes; i++) if (!(nodes[i] >= 0.0)) { g_bm_err = "nodes must be >= 0"; return BOLT_ERR_ARG; }
   for (int i = 0; i < n_k; i++) if (!(k[i] > 0.0)) { g_bm_err = "need k > 0"; return BOLT_ERR_ARG; }
   BM_CHECK(cudaSetDevice(t->device));

@@ -232,3 +232,13 @@ def test_bad_arguments_fail_loudly(B):
     itp = B.sph_bessel_interpolator(3, 2, 0.0, 100.0, 1000)
     with pytest.raises(BoltError):
         B.integrate_sph_bessel_filon(1., 0., 0., 1.0, 0., 1., itp)   # order 2 table cannot carry quadratic pieces
+
+
+def test_empty_inputs_are_no_ops(B):
+    """n = 0 everywhere: nothing launched, nothing written, no error (the reference's functions map over empty vectors)."""
+    itp = B.sph_bessel_interpolator(3, 3, 0.0, 100.0, 1000)
+    assert B._moments(3, [0, 1, 2], B.SMALL, np.zeros(0)).shape == (0, 3)
+    assert itp.many(np.zeros(0)).shape == (0, 3)
+    assert B.integrate_sph_bessel_filon(np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), itp).shape == (0,)
+    assert B.filon_chain(np.array([0.0, 1.0]), np.zeros((0, 2)), np.zeros((0, 2)), np.zeros((0, 2)), np.zeros(0), itp).shape == (0,)
+    itp.close(); itp.close()      # idempotent
