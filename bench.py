@@ -551,6 +551,21 @@ def main():
                       "max_rel_diff_tt_ee_vs_single_gpu": dev,
                       "limiter": "the longest k-mode of a shard (serial ODE steps) and the l-independent part of K2 (dense-k source "
                                  "interpolation, done by every rank), not the collectives (64 MB all-gather, 60 KB all-reduce)"}
+        # P(k) of ONE cosmology sharded the same way (bolt_plin_sharded: one all-gather, no reduction)
+        kp = np.geomspace(10 * h["bg"].H0, 5000 * h["bg"].H0, 500)
+        if strong is not None or rank != 0:
+            op = abi.make_opts(50, 50, 20, reltol=1e-5, abstol=ABSTOL)
+            dc.plin_sharded(kp, op)
+            barrier(); t0 = time.perf_counter(); pks = dc.plin_sharded(kp, op); barrier()
+            t_pk = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t_pk, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                t0 = time.perf_counter(); pk1 = dc.plin(kp, op); t_pk1 = time.perf_counter() - t0
+                strong["plin_sharded"] = {"workload": "plin, 500 log-spaced modes, n = 473, sharded over the GPUs (K1 + epilogue per shard, one ncclAllGather)",
+                                          "ms": 1e3 * float(t_pk.item()), "single_gpu_ms_same_run": 1e3 * t_pk1,
+                                          "bit_identical_to_single_gpu": bool(np.array_equal(pks[0], pk1[0])),
+                                          "note": "500 modes are less than one wave of a single GPU (1184 warp slots): the time is the longest mode's serial "
+                                                  "ODE steps on either side, so sharding buys nothing until n_k exceeds a wave"}
         barrier()
         ctx.comm_free()
 

@@ -16,7 +16,7 @@ _LIB = None
 EXPORTS = ["bolt_abi_version", "bolt_init", "bolt_finalize", "bolt_last_error", "bolt_last_timing",
            "bolt_cosmo_upload", "bolt_cosmo_free", "bolt_state_dim", "bolt_solve", "bolt_project",
            "bolt_spectra", "bolt_spectra_batch", "bolt_plin", "bolt_solve_device", "bolt_project_device", "bolt_fp64_peak", "bolt_set_bessel_xmax",
-           "bolt_comm_unique_id", "bolt_comm_init", "bolt_comm_free", "bolt_spectra_sharded", "bolt_shard_plan", "bolt_fftlog",
+           "bolt_comm_unique_id", "bolt_comm_init", "bolt_comm_free", "bolt_spectra_sharded", "bolt_plin_sharded", "bolt_shard_plan", "bolt_fftlog",
            "bolt_hostgen_batch", "bolt_hostgen_last_error",
            "bolt_sph_j_moments", "bolt_moment_table_create", "bolt_moment_table_free", "bolt_moment_table_eval",
            "bolt_filon_pieces", "bolt_filon_chain", "bolt_moments_last_error"]
@@ -58,6 +58,7 @@ def lib():
         L.bolt_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
         L.bolt_comm_free.argtypes = [vp]
         L.bolt_spectra_sharded.argtypes = L.bolt_spectra.argtypes
+        L.bolt_plin_sharded.argtypes = L.bolt_plin.argtypes
         L.bolt_shard_plan.argtypes = [dp, C.c_int, C.c_int, C.c_int, ip, ip]
         L.bolt_hostgen_batch.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, C.c_int, dp, dp, ip]
         L.bolt_hostgen_last_error.restype = C.c_char_p
@@ -265,6 +266,15 @@ class DeviceCosmo:
         st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
         self.ctx.check(lib().bolt_plin(self.ctx._h, self._h, abi.ptr(k), len(k), C.byref(opts), abi.ptr(pk),
                                        abi.ptr(st, abi.c_int32_p), abi.ptr(ns, abi.c_int64_p)))
+        return self._user(pk), st, ns
+
+    def plin_sharded(self, k, opts):
+        """bolt_plin_sharded: collective over the ranks of the context's communicator; same results as plin on every rank."""
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        pk = np.zeros(len(k) if self.hc.nd == 1 else (len(k), self.hc.nd))
+        st = np.zeros(len(k), dtype=np.int32); ns = np.zeros(len(k), dtype=np.int64)
+        self.ctx.check(lib().bolt_plin_sharded(self.ctx._h, self._h, abi.ptr(k), len(k), C.byref(opts), abi.ptr(pk),
+                                               abi.ptr(st, abi.c_int32_p), abi.ptr(ns, abi.c_int64_p)))
         return self._user(pk), st, ns
 
     # ---- device-pointer variants (torch tensors own the HBM buffers) ---------------------------------

@@ -913,6 +913,22 @@ int bolt_spectra_batch(bolt_ctx* ctx, const bolt_cosmo* const* cosmos, int ncos,
   return collect_timing(ctx);
 }
 
+// P(k) from the final state of every mode (the reference's plin epilogue, src/spectra.jl:174-198)
+static int launch_plin_epilogue(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_k, int nk, const double* d_final, const bolt_opts* o, double* d_pk) {
+  const int gb = (nk + 127) / 128;
+  switch (c->h.np) {
+    case 0: plin_kernel<<<gb, 128, 0, ctx->stream>>>(c->d, d_k, nk, d_final, o->l_gamma, o->l_nu, o->l_mnu, d_pk); break;
+    case 1: plin_kernel_d<1><<<gb, 128, 0, ctx->stream>>>(c->d, d_k, nk, d_final, o->l_gamma, o->l_nu, o->l_mnu, d_pk); break;
+    case 2: plin_kernel_d<2><<<gb, 128, 0, ctx->stream>>>(c->d, d_k, nk, d_final, o->l_gamma, o->l_nu, o->l_mnu, d_pk); break;
+    case 3: plin_kernel_d<3><<<gb, 128, 0, ctx->stream>>>(c->d, d_k, nk, d_final, o->l_gamma, o->l_nu, o->l_mnu, d_pk); break;
+    case 4: plin_kernel_d<4><<<gb, 128, 0, ctx->stream>>>(c->d, d_k, nk, d_final, o->l_gamma, o->l_nu, o->l_mnu, d_pk); break;
+    case 6: plin_kernel_d<6><<<gb, 128, 0, ctx->stream>>>(c->d, d_k, nk, d_final, o->l_gamma, o->l_nu, o->l_mnu, d_pk); break;
+    default: return fail(ctx, BOLT_ERR_UNSUPPORTED, "this build carries 1, 2, 3, 4 or 6 partials per call");
+  }
+  CUDA_OK(cudaGetLastError());
+  return BOLT_OK;
+}
+
 int bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o, double* pk, int32_t* status,
               int64_t* nsteps) {
   if (!ctx) return BOLT_ERR_ARG;
@@ -931,17 +947,7 @@ int bolt_plin(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const
   bolt_opts oo = *o; oo.ix_first = c->h.n_x;   // plin only needs perturb(0): no source sampling
   rc = launch_hierarchy(ctx, c, d_k.p, d_order.p, nk, &oo, nullptr, nullptr, nullptr, d_final.p, d_status.p, d_ns.p, nullptr);
   if (rc) return rc;
-  const int gb = (nk + 127) / 128;
-  switch (c->h.np) {
-    case 0: plin_kernel<<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
-    case 1: plin_kernel_d<1><<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
-    case 2: plin_kernel_d<2><<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
-    case 3: plin_kernel_d<3><<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
-    case 4: plin_kernel_d<4><<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
-    case 6: plin_kernel_d<6><<<gb, 128, 0, ctx->stream>>>(c->d, d_k.p, nk, d_final.p, o->l_gamma, o->l_nu, o->l_mnu, d_pk.p); break;
-    default: return fail(ctx, BOLT_ERR_UNSUPPORTED, "this build carries 1, 2, 3, 4 or 6 partials per call");
-  }
-  CUDA_OK(cudaGetLastError());
+  rc = launch_plin_epilogue(ctx, c, d_k.p, nk, d_final.p, o, d_pk.p); if (rc) return rc;
   CUDA_OK(cudaMemcpyAsync(pk, d_pk.p, (size_t)nk * nd * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CUDA_OK(cudaMemcpyAsync(status, d_status.p, nk * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (nsteps) CUDA_OK(cudaMemcpyAsync(nsteps, d_ns.p, nk * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1165,6 +1171,65 @@ int bolt_spectra_sharded(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, in
     if (status) status[ik] = h_st[(size_t)r * per + j];
     if (nsteps) nsteps[ik] = h_cnt[((size_t)r * 2) * per + j];
     if (nreject) nreject[ik] = h_cnt[((size_t)r * 2 + 1) * per + j];
+  }
+  return collect_timing(ctx);
+}
+
+// plin over several GPUs ("P(k): no reduction, ncclAllGather of [nd][n_k]"): K1 + the epilogue on this rank's cyclic shard
+// of the descending-k order, one all-gather of the P(k) rows (and of status / step counts), un-sharded on the host.
+int bolt_plin_sharded(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o, double* pk, int32_t* status,
+                      int64_t* nsteps) {
+  if (!ctx) return BOLT_ERR_ARG;
+  if (!ctx->comm || ctx->nranks == 1) return bolt_plin(ctx, c, k, nk, o, pk, status, nsteps);
+  if (!c || !k || nk < 1 || !pk) return fail(ctx, BOLT_ERR_ARG, "bad arguments");
+  int rc = check_opts(ctx, c, o); if (rc) return rc;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  reset_timing(ctx);
+  CUDA_OK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const int R = ctx->nranks, rank = ctx->rank, nd = c->h.nd;
+  const int n = bolt_state_dim(o->l_gamma, o->l_nu, o->l_mnu, c->h.nq);
+  const int per = (nk + R - 1) / R;
+  std::vector<int> order(nk);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return k[a] > k[b]; });
+  std::vector<double> kloc; std::vector<int> ident;
+  for (int pos = rank; pos < nk; pos += R) { kloc.push_back(k[order[pos]]); ident.push_back((int)ident.size()); }
+  const int nloc = (int)kloc.size();
+  DevBuf<double> d_kloc, d_final, d_pk_loc, d_pk_all; DevBuf<int> d_ident, d_st_loc, d_st_all; DevBuf<long long> d_ns_loc, d_ns_all;
+  CUDA_OK(d_kloc.alloc(ctx, std::max(nloc, 1))); CUDA_OK(d_ident.alloc(ctx, std::max(nloc, 1)));
+  if (nloc) {
+    CUDA_OK(cudaMemcpyAsync(d_kloc.p, kloc.data(), nloc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(d_ident.p, ident.data(), nloc * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));     // host vectors are locals
+  CUDA_OK(d_final.alloc(ctx, (size_t)std::max(nloc, 1) * n * nd));
+  CUDA_OK(d_pk_loc.alloc(ctx, (size_t)per * nd)); CUDA_OK(d_pk_all.alloc(ctx, (size_t)R * per * nd));
+  CUDA_OK(d_st_loc.alloc(ctx, per)); CUDA_OK(d_st_all.alloc(ctx, (size_t)R * per));
+  CUDA_OK(d_ns_loc.alloc(ctx, per)); CUDA_OK(d_ns_all.alloc(ctx, (size_t)R * per));
+  CUDA_OK(cudaMemsetAsync(d_final.p, 0, d_final.n * 8, ctx->stream));
+  CUDA_OK(cudaMemsetAsync(d_pk_loc.p, 0, d_pk_loc.n * 8, ctx->stream));
+  CUDA_OK(cudaMemsetAsync(d_st_loc.p, 0, per * sizeof(int), ctx->stream));
+  CUDA_OK(cudaMemsetAsync(d_ns_loc.p, 0, per * sizeof(long long), ctx->stream));
+  if (nloc) {
+    bolt_opts oo = *o; oo.ix_first = c->h.n_x;
+    rc = launch_hierarchy(ctx, c, d_kloc.p, d_ident.p, nloc, &oo, nullptr, nullptr, nullptr, d_final.p, d_st_loc.p, d_ns_loc.p, nullptr);
+    if (rc) return bail(ctx, rc);
+    rc = launch_plin_epilogue(ctx, c, d_kloc.p, nloc, d_final.p, o, d_pk_loc.p); if (rc) return bail(ctx, rc);
+  }
+  NCCL_OK(g_nccl.AllGather(d_pk_loc.p, d_pk_all.p, (size_t)per * nd, NCCL_FLOAT64, ctx->comm, ctx->stream), "ncclAllGather(P(k))");
+  NCCL_OK(g_nccl.AllGather(d_st_loc.p, d_st_all.p, (size_t)per, NCCL_INT32, ctx->comm, ctx->stream), "ncclAllGather(status)");
+  NCCL_OK(g_nccl.AllGather(d_ns_loc.p, d_ns_all.p, (size_t)per, NCCL_INT64, ctx->comm, ctx->stream), "ncclAllGather(step counts)");
+  std::vector<double> h_pk((size_t)R * per * nd); std::vector<int> h_st((size_t)R * per); std::vector<long long> h_ns((size_t)R * per);
+  CUDA_OK(cudaMemcpyAsync(h_pk.data(), d_pk_all.p, h_pk.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(h_st.data(), d_st_all.p, h_st.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(h_ns.data(), d_ns_all.p, h_ns.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  for (int pos = 0; pos < nk; pos++) {
+    const int r = pos % R, j = pos / R, ik = order[pos];
+    for (int d = 0; d < nd; d++) pk[(size_t)ik * nd + d] = h_pk[((size_t)r * per + j) * nd + d];
+    if (status) status[ik] = h_st[(size_t)r * per + j];
+    if (nsteps) nsteps[ik] = h_ns[(size_t)r * per + j];
   }
   return collect_timing(ctx);
 }

@@ -352,6 +352,21 @@ function spectra_sharded(‚Ñì‚Éó, ùï°::AbstractCosmoParams{T}, bg, ih, k_grid; ‚
     end
 end
 
+"""`plin` of ONE cosmology over the ranks of the communicator (comm_init): K1 and the P(k) epilogue on each rank's shard, one
+ncclAllGather; same result on every rank as `plin(ks, ùï°, bg, ih, ‚Ä¶)` (x = 0)."""
+function plin_sharded(ks::AbstractVector, ùï°::AbstractCosmoParams{T}, bg, ih, n_q=15, ‚Ñì·µß=50, ‚Ñì_ŒΩ=50, ‚Ñì_mŒΩ=20, reltol=1e-5; dev=Device()) where T
+    n_q == length(bg.quad_pts) || error("n_q must match the background's quadrature")
+    o = adaptive(‚Ñì·µß, ‚Ñì_ŒΩ, ‚Ñì_mŒΩ, reltol, 1e-6)
+    with_cosmo(dev, ùï°, bg, ih) do ctx, c, nd
+        k = plain(ks); nk = length(k)
+        pk = zeros(Float64, nd * nk); status = zeros(Int32, nk); nsteps = zeros(Int64, nk)
+        GC.@preserve k pk status nsteps check(ctx, ccall((:bolt_plin_sharded, lib), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Cint, Ref{Opts}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}), ctx, c, k, nk, o, pk, status, nsteps))
+        warn_status(status, "bolt_plin_sharded")
+        unflat(T, pk, nd)
+    end
+end
+
 """FFTLog on the device (src/util.jl:33-108): `plan_fftlog(r, Œº, q, k‚ÇÄr‚ÇÄ; kropt)` followed by `mul!` (inverse = false) or `ldiv!`.
 Returns (y::Vector{ComplexF64}, k::Vector{Float64}).  N must be a power of two ‚â§ 4096."""
 function fftlog(r::AbstractVector, a::AbstractVector, Œº, q, k‚ÇÄr‚ÇÄ=1.0; kropt=true, inverse=false, dev=Device())

@@ -171,6 +171,8 @@ int  bolt_project_device(bolt_ctx* ctx, const bolt_cosmo* c, const double* d_S_T
  *   bolt_spectra_sharded  same arguments and results as bolt_spectra on EVERY rank.  K1 on the rank's cyclic shard of the
  *                         descending-k order, one ncclAllGather of the source columns, K2 on multipoles rank, rank+R, ...,
  *                         ONE ncclAllReduce(sum, double) of the C_l vector; all on the context's stream.
+ *   bolt_plin_sharded     same arguments and results as bolt_plin on EVERY rank: K1 and the P(k) epilogue on the rank's shard, ONE
+ *                         ncclAllGather of the [n_local][nd] rows (+ status and step counts); no reduction.
  *   bolt_shard_plan       (host only, no device needed) the indices into k[] that rank `rank` of `nranks` solves, in work order. */
 int  bolt_comm_unique_id(bolt_ctx* ctx, void* id128);
 int  bolt_comm_init(bolt_ctx* ctx, int rank, int nranks, const void* id128);
@@ -179,6 +181,8 @@ int  bolt_spectra_sharded(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, i
                           const int32_t* ell, int nell, double kd_min, double kd_max, int n_kd, int ix_start,
                           double* cl_tt, double* cl_te, double* cl_ee,
                           int32_t* status, int64_t* nsteps, int64_t* nreject);
+int  bolt_plin_sharded(bolt_ctx* ctx, const bolt_cosmo* c, const double* k, int nk, const bolt_opts* o,
+                       double* pk, int32_t* status, int64_t* nsteps);
 int  bolt_shard_plan(const double* k, int nk, int rank, int nranks, int32_t* idx, int32_t* n_local);
 
 /* FFTLog (src/util.jl:33-108: plan_fftlog + mul! / ldiv!), SURVEY 8f row n4: the biased Hankel-type transform of a[N] sampled on

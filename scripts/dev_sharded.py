@@ -51,6 +51,18 @@ if rank == 0:
     for nm, a, b in (("tt", tt, r[0]), ("te", te, r[1]), ("ee", ee, r[2])):
         print(nm, "max rel diff sharded vs single: %.3e" % np.abs(a / b - 1).max())
     print("status equal", np.array_equal(st, r[3]), "nsteps equal", np.array_equal(ns, r[4]))
+# plin (BASELINE config 2): 500 modes, 50/50/20, sharded with one all-gather
+kp = B.log10_k(10 * bg.H0, 5000 * bg.H0, 500)
+op = abi.make_opts(50, 50, 20, reltol=1e-5, abstol=1e-6)
+for rep in range(3):
+    barrier(); t0 = time.perf_counter()
+    pk, stp, nsp = dc.plin_sharded(kp, op)
+    barrier(); dtp = time.perf_counter() - t0
+if rank == 0:
+    for rep in range(2):
+        t0 = time.perf_counter(); pk1, st1, ns1 = dc.plin(kp, op); dt1 = time.perf_counter() - t0
+    print("plin sharded x%d: %.2f ms; single GPU %.2f ms; bit-identical %s, status equal %s, nsteps equal %s" % (
+        world, 1e3 * dtp, 1e3 * dt1, np.array_equal(pk, pk1), np.array_equal(stp, st1), np.array_equal(nsp, ns1)), flush=True)
 barrier()
 if world > 1:
     ctx.comm_free()
