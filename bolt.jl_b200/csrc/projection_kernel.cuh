@@ -176,6 +176,16 @@ struct ProjectParams {
   double* partial;         // [nell][nsplit][3]
 };
 
+#ifndef K2_WINDOW_SHIFTS
+#define K2_WINDOW_SHIFTS 0
+#endif
+#ifndef K2_WINDOW
+#define K2_WINDOW 1
+#endif
+#ifndef K2_ROW_UNROLL
+#define K2_ROW_UNROLL 2
+#endif
+constexpr int k2_row_unroll = K2_ROW_UNROLL;
 template <int NL, int NT>
 __global__ void __launch_bounds__(NT) project_kernel(ProjectParams p) {
   extern __shared__ __align__(128) double smem[];
@@ -202,14 +212,17 @@ __global__ void __launch_bounds__(NT) project_kernel(ProjectParams p) {
 #pragma unroll
     for (int l = 0; l < NL; l++) { th[l] = 0; ep[l] = 0; }
     const double* sT = p.SD_T + j; const double* sP = p.SD_P + j;
-    // Sliding window over the four spline coefficients: chi_i decreases with i, so the table cell ii never increases, and for
-    // most (k, x) pairs it moves by 0-2 cells between consecutive rows (it moves by ks * dchi / dg).  The kernel is bound by its
-    // shared-memory gathers (8 wavefronts per warp-evaluation are bytes), so the coefficients that stay are kept in registers
-    // and only the new ones are fetched; adjacent k share the slide to within one cell, so the cases barely diverge in a warp.
-    // Same operands, same operation order: bit-identical to fetching all four every time.
+    // Coefficient window: chi_i decreases with i, so the table cell ii never increases, and for ~40 % of the (k, x) pairs it does
+    // not move at all between consecutive rows (it moves by ks * dchi / dg).  The four coefficients of each multipole are kept in
+    // registers and re-read from shared memory only when the cell changes -- same operands, same operation order: bit-identical
+    // to fetching all four every time.  Measured (2000-mode C3 grid, row loop unrolled by 2 in every case): no window 14.8 ms;
+    // re-read on any move (this) 13.0 ms; additionally SHIFTING the window by one or two cells (K2_WINDOW_SHIFTS=1: fewer shared
+    // loads, but 24-34 register moves per shift and a warp executes the union of its lanes' cases) 13.9 ms.  Unrolling the row
+    // loop by 2 lets the next row's argument / weight arithmetic overlap the current row's loads (13.7 -> 13.0 ms; by 4 the
+    // kernel hits the 128-register cap of a 512-thread CTA: 14.1 ms).
     double cw[NL][4];
     int ii_prev = -1000;
-#pragma unroll 1
+#pragma unroll (k2_row_unroll)
     for (int i = 0; i < p.nrows; i++) {
       const double t = ks * chi[i];
       int ii = (int)t;                       // t >= 0: truncation == floor
@@ -223,15 +236,18 @@ __global__ void __launch_bounds__(NT) project_kernel(ProjectParams p) {
       const double vT = hasT ? __ldg(sT + (size_t)i * p.ld) : 0.0;
       const double vP = hasP ? __ldg(sP + (size_t)i * p.ld) : 0.0;
       const int delta = ii_prev - ii;
-      if (delta != 0) {
+      if (!K2_WINDOW || delta != 0) {
         const double* c = tabs + ii;
+#if K2_WINDOW_SHIFTS
         if (delta == 1) {
 #pragma unroll
           for (int l = 0; l < NL; l++) { cw[l][3] = cw[l][2]; cw[l][2] = cw[l][1]; cw[l][1] = cw[l][0]; cw[l][0] = c[l * BESSEL_NC]; }
         } else if (delta == 2) {
 #pragma unroll
           for (int l = 0; l < NL; l++) { cw[l][3] = cw[l][1]; cw[l][2] = cw[l][0]; cw[l][1] = c[l * BESSEL_NC + 1]; cw[l][0] = c[l * BESSEL_NC]; }
-        } else {
+        } else
+#endif
+        {
 #pragma unroll
           for (int l = 0; l < NL; l++) { cw[l][0] = c[l * BESSEL_NC]; cw[l][1] = c[l * BESSEL_NC + 1]; cw[l][2] = c[l * BESSEL_NC + 2]; cw[l][3] = c[l * BESSEL_NC + 3]; }
         }
