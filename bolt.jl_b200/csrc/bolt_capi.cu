@@ -368,7 +368,11 @@ int collect_timing(bolt_ctx* ctx) {
 }
 void reset_timing(bolt_ctx* ctx) { for (int i = 0; i < 8; i++) ctx->timing[i] = 0; }
 
-constexpr int PROJ_NL = 4, PROJ_NT = 512;
+#ifndef K2_NL
+#define K2_NL 4
+#define K2_NT 512
+#endif
+constexpr int PROJ_NL = K2_NL, PROJ_NT = K2_NT;
 
 constexpr int PROJD_NL = 2, PROJD_NT = 256;
 

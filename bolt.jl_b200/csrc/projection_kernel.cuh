@@ -187,7 +187,7 @@ struct ProjectParams {
 #endif
 constexpr int k2_row_unroll = K2_ROW_UNROLL;
 template <int NL, int NT>
-__global__ void __launch_bounds__(NT) project_kernel(ProjectParams p) {
+__global__ void __launch_bounds__(NT, (NL <= 2 ? 2 : 1)) project_kernel(ProjectParams p) {
   extern __shared__ __align__(128) double smem[];
   double* tabs = smem;                                   // [NL][BESSEL_NC]
   double* chi = smem + (size_t)NL * BESSEL_NC;           // [nrows]
