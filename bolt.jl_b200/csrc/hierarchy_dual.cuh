@@ -381,9 +381,12 @@ __device__ __forceinline__ void initial_conditions_d(const DevCosmo& c, const La
 template <int NP>
 __device__ __forceinline__ void sample_sources_d(const DevCosmo& c, const Lane& ln, const SolveParams& p, int ik, int ix, double xs,
                                                  const Hermite& hm, const DArr<NP>& u0, const DArr<NP>& u1, const DArr<NP>& z1, double s1,
-                                                 const DArr<NP>& z6, bool& rsa_flag) {
+                                                 const DArr<NP>& z6, bool& rsa_flag, bool write_value = true, const int* cmap = nullptr) {
+  // write_value / cmap: the CTA-per-mode kernel samples every partial on the warp that owns it (NP = 1 on a single-partial view):
+  // that warp writes only its partial, into the output slot cmap[0]
   typedef Dual<NP> T;
   constexpr int ND = 1 + NP;
+  const int* const cm = cmap ? cmap : p.comp_map;
   auto herm = [&](int idx) { return hm.c0 * u0.get(idx) + hm.c1 * u1.get(idx) + (hm.d0 * s1) * z1.get(idx) + hm.d1 * z6.get(idx); };
   if (!p.S_T && !p.S_P) return;
   BgD<NP> b; eval_bg_d<NP>(c, ln, xs, b);
@@ -444,12 +447,12 @@ __device__ __forceinline__ void sample_sources_d(const DevCosmo& c, const Lane& 
   if (ln.lane == 0) {
     const T sT = term1 + term2 + term3;
     const T sP = (3.0 / (4.0 * y * y)) * g * Pi;
-    if (p.S_T) { double* o = p.S_T + ((size_t)ik * c.n_x + ix) * p.out_nd; o[0] = sT.v;
+    if (p.S_T) { double* o = p.S_T + ((size_t)ik * c.n_x + ix) * p.out_nd; if (write_value) o[0] = sT.v;
 #pragma unroll
-      for (int j = 0; j < NP; j++) o[p.comp_map[j]] = sT.d[j]; }
-    if (p.S_P) { double* o = p.S_P + ((size_t)ik * c.n_x + ix) * p.out_nd; o[0] = sP.v;
+      for (int j = 0; j < NP; j++) o[cm[j]] = sT.d[j]; }
+    if (p.S_P) { double* o = p.S_P + ((size_t)ik * c.n_x + ix) * p.out_nd; if (write_value) o[0] = sP.v;
 #pragma unroll
-      for (int j = 0; j < NP; j++) o[p.comp_map[j]] = sP.d[j]; }
+      for (int j = 0; j < NP; j++) o[cm[j]] = sP.d[j]; }
   }
 }
 

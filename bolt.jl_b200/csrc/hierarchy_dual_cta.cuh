@@ -289,16 +289,6 @@ __global__ void __launch_bounds__(32 * (1 + NP), (NP <= 4) ? 2 : 1) hierarchy_du
           if (accept) {
             const bool last = fixed ? (fixed_left == 1) : clamped;
             const double xn1 = last ? x_end : (fixed ? (x_begin + (double)(fixed_total - fixed_left + 1) * p.fixed_dt) : (x + dt));
-            while (ix < c.n_x) {
-              const double xq = c.x0 + c.dx * ix;
-              if (!last && xq > xn1 + 1e-12) break;
-              if (ix >= p.ix_first) {
-                double th = (xq - x) / dt; if (th > 1.0) th = 1.0;
-                Hermite hm = hermite_weights(th);
-                sample_sources_d<NP>(c, ln, p, ik, ix, xq, hm, U, Z1, Z0, s1, Z5, rsa_flag);
-              }
-              ix++;
-            }
             xn = xn1;
             if (fixed) s1n = 1.0;
             else {
@@ -323,7 +313,29 @@ __global__ void __launch_bounds__(32 * (1 + NP), (NP <= 4) ? 2 : 1) hierarchy_du
         const int st = (int)ctrl[5];
         if (st != BOLT_K_OK) { status = st; break; }
         if (accept) {
-          x = ctrl[4]; nsteps++;
+          // dense output on the grid rows this step crossed: EVERY warp samples its own component (warp 0 the value, warp j the
+          // Dual<1> sources of its partial on its single-partial view) instead of warp 0 doing all 1 + NP while the others wait
+          const bool last = fixed ? (fixed_left == 1) : clamped;
+          const double xn1 = ctrl[4];
+          bool sampled = false;
+          while (ix < c.n_x) {
+            const double xq = c.x0 + c.dx * ix;
+            if (!last && xq > xn1 + 1e-12) break;
+            if (ix >= p.ix_first) {
+              double th = (xq - x) / dt; if (th > 1.0) th = 1.0;
+              Hermite hm = hermite_weights(th);
+              if (warp == 0) sample_sources(c, ln, p, ik, ix, xq, hm, U.p, Z1.p, Z0.p, s1, Z5.p, rsa_flag, &mc);
+              else {
+                const int cs = warp * na;      // Dual<1> view of (value, this warp's partial) of every state array
+                sample_sources_d<1>(cj, ln, p, ik, ix, xq, hm, DArr<1>{U.p, cs}, DArr<1>{Z1.p, cs}, DArr<1>{Z0.p, cs}, s1, DArr<1>{Z5.p, cs},
+                                    rsa_flag, false, &p.comp_map[warp - 1]);
+              }
+              sampled = true;
+            }
+            ix++;
+          }
+          if (sampled) dcta_sync(NTH);        // nobody overwrites u_n / z_1 (next step's stage 1) before every warp has read them
+          x = xn1; nsteps++;
           flipU = !flipU; flipZ = !flipZ; U = CSL_U; Z1 = CSL_Z1; Z0 = CSL_Z0; Z5 = CSL_Z5;
           if (fixed) fixed_left--;
         } else nreject++;
