@@ -126,3 +126,33 @@ def test_adaptive_gradients_agree_with_fixed_step(dual_setup):
         assert (np.abs(x[:, 0] - y[:, 0]) / sc).max() < 2e-3
         # gradient error in units of C_ℓ/p, i.e. the error of dlnC_ℓ/dlnp
         assert (np.abs(x[:, 1:] - y[:, 1:]) * np.abs(pvals)[None, :] / sc[:, None]).max() < 2e-3
+
+
+def test_cta_kernel_matches_one_warp_kernel_in_every_component(dual_setup, monkeypatch):
+    """K1 with partials has two implementations: one CTA per mode (value warp + one warp per sensitivity system, every warp
+    sampling the sources of its own component) and the one-warp kernel (BOLT_K1_DUAL_WARP=1: all systems in sequence, sources
+    sampled in Dual<NP> arithmetic).  Same mathematics: fixed-step results agree to rounding in every component of S_T, S_P and
+    the final state; adaptive runs take identical step sequences."""
+    from bolt_b200 import abi
+    par, bg, dev, steps = dual_setup
+    ks = np.array([0.5, 30.0, 300.0, 900.0]) * bg.H0
+
+    def both(o):
+        monkeypatch.delenv("BOLT_K1_DUAL_WARP", raising=False)
+        a = dev["dual"].solve(ks, o, want=("S_T", "S_P", "u_final"))
+        monkeypatch.setenv("BOLT_K1_DUAL_WARP", "1")
+        b = dev["dual"].solve(ks, o, want=("S_T", "S_P", "u_final"))
+        monkeypatch.delenv("BOLT_K1_DUAL_WARP", raising=False)
+        return a, b
+
+    a, b = both(abi.make_opts(8, 8, 10, fixed_dt=0.01))
+    assert np.all(a["status"] == 0) and np.all(b["status"] == 0)
+    for comp in range(1 + len(NAMES)):
+        for key, sl in (("S_T", np.s_[:, :, comp]), ("S_P", np.s_[:, :-1, comp]), ("u_final", np.s_[..., comp])):
+            x, y = a[key][sl], b[key][sl]
+            assert np.abs(x - y).max() <= 1e-8 * np.abs(y).max(), (key, comp)
+    a, b = both(abi.make_opts(8, 8, 10, reltol=1e-9, abstol=1e-6, ix_first=1201))
+    assert np.array_equal(a["nsteps"], b["nsteps"]) and np.array_equal(a["status"], b["status"])
+    for comp in range(1 + len(NAMES)):
+        x, y = a["S_T"][:, 1201:, comp], b["S_T"][:, 1201:, comp]
+        assert np.abs(x - y).max() <= 1e-6 * np.abs(y).max(), comp
