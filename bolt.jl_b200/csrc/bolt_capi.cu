@@ -374,7 +374,7 @@ void reset_timing(bolt_ctx* ctx) { for (int i = 0; i < 8; i++) ctx->timing[i] = 
 #endif
 constexpr int PROJ_NL = K2_NL, PROJ_NT = K2_NT;
 
-constexpr int PROJD_NL = 2, PROJD_NT = 256;
+constexpr int PROJD_NL = 2, PROJD_NT = 384;
 
 template <int NP>
 int launch_project_dual(bolt_ctx* ctx, const ProjectParamsD& pd, int groups, int nsplit, size_t smem) {

@@ -370,16 +370,17 @@ __global__ void __launch_bounds__(NT) project_kernel_dual(ProjectParamsD pd) {
   __syncthreads();
   const int per = (p.nkd1 + p.nsplit - 1) / p.nsplit;
   const int jbeg = split * per, jend = min(p.nkd1, jbeg + per);
-  double acc[3][NL][1 + NP];
-#pragma unroll
-  for (int a = 0; a < 3; a++)
-#pragma unroll
-    for (int l = 0; l < NL; l++)
-#pragma unroll
-      for (int q = 0; q <= NP; q++) acc[a][l][q] = 0.0;
+  // The 3 x NL x (1+NP) accumulators of a thread (42 doubles at NL = 2, NP = 6) would be live through the whole row loop; they are
+  // needed once per dense wavenumber only, so each warp keeps ITS sums in shared memory (red[.][warp]) and adds the warp-reduced
+  // contribution of every k-iteration there (42 reductions per ~120k row-loop instructions): 239 -> fewer registers, 8 -> 12 warps.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = lane; i < 3 * NL * (1 + NP); i += 32) red[i][warp] = 0.0;
+  __syncwarp();
   const bool hasT = p.SD_T != nullptr, hasP = p.SD_P != nullptr;
   const size_t cstr = (size_t)p.nrows * p.ld;
-  for (int j = jbeg + threadIdx.x; j < jend; j += NT) {
+  for (int j0 = jbeg; j0 < jend; j0 += NT) {       // warp-uniform trip count: every lane takes part in the reductions
+    const int j = min(j0 + (int)threadIdx.x, jend - 1);
+    const bool livej = j0 + (int)threadIdx.x < jend;
     const double ks = p.kscaled[j];
     double th[NL][1 + NP], ep[NL][1 + NP];
 #pragma unroll
@@ -417,30 +418,24 @@ __global__ void __launch_bounds__(NT) project_kernel_dual(ProjectParamsD pd) {
         }
       }
     }
-    const double w = p.wk[j];
+    const double w = livej ? p.wk[j] : 0.0;
+    auto add = [&](int a, int l, int q, double v) {
+      const double sv = warp_sum(v);
+      if (lane == 0) red[(a * NL + l) * (1 + NP) + q][warp] += sv;
+    };
 #pragma unroll
     for (int l = 0; l < NL; l++) {
       const double T0 = th[l][0], E0 = ep[l][0];
-      acc[0][l][0] += T0 * T0 * w; acc[1][l][0] += T0 * E0 * w; acc[2][l][0] += E0 * E0 * w;
+      add(0, l, 0, T0 * T0 * w); add(1, l, 0, T0 * E0 * w); add(2, l, 0, E0 * E0 * w);
 #pragma unroll
       for (int q = 0; q < NP; q++) {
-        const double dw = pd.dwk[(size_t)q * p.nkd1 + j];
-        acc[0][l][1 + q] += 2.0 * T0 * th[l][1 + q] * w + T0 * T0 * dw;
-        acc[1][l][1 + q] += (th[l][1 + q] * E0 + T0 * ep[l][1 + q]) * w + T0 * E0 * dw;
-        acc[2][l][1 + q] += 2.0 * E0 * ep[l][1 + q] * w + E0 * E0 * dw;
+        const double dw = livej ? pd.dwk[(size_t)q * p.nkd1 + j] : 0.0;
+        add(0, l, 1 + q, 2.0 * T0 * th[l][1 + q] * w + T0 * T0 * dw);
+        add(1, l, 1 + q, (th[l][1 + q] * E0 + T0 * ep[l][1 + q]) * w + T0 * E0 * dw);
+        add(2, l, 1 + q, 2.0 * E0 * ep[l][1 + q] * w + E0 * E0 * dw);
       }
     }
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int a = 0; a < 3; a++)
-#pragma unroll
-    for (int l = 0; l < NL; l++)
-#pragma unroll
-      for (int q = 0; q <= NP; q++) {
-        const double s = warp_sum(acc[a][l][q]);
-        if (lane == 0) red[(a * NL + l) * (1 + NP) + q][warp] = s;
-      }
   __syncthreads();
   if (threadIdx.x < 3 * NL * (1 + NP)) {
     double s = 0.0;
