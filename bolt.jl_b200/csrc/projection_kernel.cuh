@@ -202,11 +202,14 @@ __global__ void __launch_bounds__(NT, (NL <= 2 ? 2 : 1)) project_kernel(ProjectP
 
   const int per = (p.nkd1 + p.nsplit - 1) / p.nsplit;
   const int jbeg = split * per, jend = min(p.nkd1, jbeg + per);
-  double stt[NL], ste[NL], see[NL];
-#pragma unroll
-  for (int l = 0; l < NL; l++) { stt[l] = 0; ste[l] = 0; see[l] = 0; }
+  // per-warp sums in shared memory (red[.][warp]); each k-iteration adds its warp-reduced contribution (see project_kernel_dual)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = lane; i < 3 * NL; i += 32) red[i][warp] = 0.0;
+  __syncwarp();
   const bool hasT = p.SD_T != nullptr, hasP = p.SD_P != nullptr;
-  for (int j = jbeg + threadIdx.x; j < jend; j += NT) {
+  for (int j0 = jbeg; j0 < jend; j0 += NT) {         // warp-uniform trip count: every lane takes part in the reductions
+    const int j = min(j0 + (int)threadIdx.x, jend - 1);
+    const bool livej = j0 + (int)threadIdx.x < jend;
     const double ks = p.kscaled[j];
     double th[NL], ep[NL];
 #pragma unroll
@@ -260,17 +263,14 @@ __global__ void __launch_bounds__(NT, (NL <= 2 ? 2 : 1)) project_kernel(ProjectP
         ep[l] += bes * vP;
       }
     }
-    const double w = p.wk[j];
+    const double w = livej ? p.wk[j] : 0.0;
 #pragma unroll
-    for (int l = 0; l < NL; l++) { stt[l] += th[l] * th[l] * w; ste[l] += th[l] * ep[l] * w; see[l] += ep[l] * ep[l] * w; }
+    for (int l = 0; l < NL; l++) {
+      const double a = warp_sum(th[l] * th[l] * w), b = warp_sum(th[l] * ep[l] * w), c = warp_sum(ep[l] * ep[l] * w);
+      if (lane == 0) { red[3 * l][warp] += a; red[3 * l + 1][warp] += b; red[3 * l + 2][warp] += c; }
+    }
   }
   // block reduction (fixed order: deterministic)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int l = 0; l < NL; l++) {
-    const double a = warp_sum(stt[l]), b = warp_sum(ste[l]), c = warp_sum(see[l]);
-    if (lane == 0) { red[3 * l][warp] = a; red[3 * l + 1][warp] = b; red[3 * l + 2][warp] = c; }
-  }
   __syncthreads();
   if (threadIdx.x < 3 * NL) {
     double s = 0.0;
