@@ -628,8 +628,8 @@ def main():
         k2_bytes = (2 * 799 * 4999 * 8) + nell * 5003 * 8      # one read of the dense source grids + the spline tables
         k2_terms = 2.0 * nell * 4999 * 799
         roof_k2 = {"kernel": "project_kernel (K2)", "bound": "hbm", "achieved": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                   "unit": "GB/s", "frac": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": 2.94e8,
-                   "traffic_note": "NOT measured in this run: one ncu --set full capture (profiles/r2/k2_projection.md): 288 MB read + 5.7 MB written per launch",
+                   "unit": "GB/s", "frac": k2_bytes * args.steps / (k2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": 2.95e8,
+                   "traffic_note": "NOT measured in this run: one ncu --set full capture of the shipped kernel (profiles/r2/k2_projection_final.md): 291 MB read + 4.4 MB written per launch",
                    "fp64_tflops": 25.0 * k2_terms / 2 * args.steps / (k2_ms * 1e-3) / 1e12,
                    "note": "K2 is FP64/shared-memory-gather bound, not HBM bound (SURVEY 8d): both figures reported"}
         line = {"metric": "kmode_hierarchy_solves_per_s", "value": value, "unit": "k-mode solves/s", "n_gpus": world, "steps": args.steps,
