@@ -612,7 +612,7 @@ def main():
         total_solves = NK * args.steps * world
         value = total_solves / wall_max
         fl = nstep_tot * f_step(n)        # accepted + rejected step attempts (bolt_spectra returns both counts)
-        roof = {"kernel": "hierarchy_kernel_t<Trunc<8,8,10,15,19>, 4> (K1, dominant: 73 % of the step)", "bound": "fp64", "achieved": fl / (k1_ms * 1e-3) / 1e12, "peak": fp64_peak,
+        roof = {"kernel": "hierarchy_kernel_t<Trunc<8,8,10,15,19>, 4> (K1, dominant: 75 % of the step)", "bound": "fp64", "achieved": fl / (k1_ms * 1e-3) / 1e12, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": fl / (k1_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
                 "traffic": 4.5e5, "traffic_note": "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel "
                                                   "on the same 2000-mode grid (profiles/r2/k1_warp_lockstep_2000modes.md, round 2): 295 KB + 156 KB per launch -- "
