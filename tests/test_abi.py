@@ -57,6 +57,17 @@ def test_no_cpu_fallback_without_device():
     import bolt_b200 as B
     with pytest.raises(capi.BoltError):
         B.default_context()
+    # the context-free entry points (batched input tables, Bessel moments / Filon rule) select a device themselves: same rule
+    import numpy as np
+    import bolt_b200.bessel as BM
+    with pytest.raises(capi.BoltError):
+        capi.hostgen_batch([B.CosmoParams()])
+    with pytest.raises(capi.BoltError):
+        BM.sph_bessel_interpolator(3, 3, 0.0, 100.0, 1000)
+    with pytest.raises(capi.BoltError):
+        BM.sph_j_moment_asymp(200.0, 2, 0)
+    with pytest.raises(capi.BoltError):
+        BM._moments(2, [0, 1, 2], BM.SMALL, np.array([1.0, 10.0]))
 
 
 def test_product_does_not_import_oracle():
