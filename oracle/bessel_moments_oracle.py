@@ -6,9 +6,11 @@ Restates, function by function, the reference's
   src/bessel/moments.jl      (moments  ∫₀ˣ tᵐ j_ν(t) dt  and  ∫₀ˣ t^α J_ν(t) dt)
   src/bessel/interpolator.jl (MomentTable: cubic B-spline table of the moments + Maclaurin / Lommel branches outside it)
   src/bessel/integrator.jl   (Filon rule: quadratic source piece × j_ν(kx) integrated with the moments)
-One deliberate difference: the reference sums the ₁F₂ of moments.jl:24-27,72-76 with Weniger's sequence transformation in
-Double64 (src/bessel/weniger.jl:50-235); this oracle sums the SAME ₁F₂ with mpmath at 40 digits.  Both are evaluations of one
-function; the oracle is pinned by the reference's own big-float known answers (test/testbessel.jl, every testset), see
+  src/bessel/weniger.jl      (weniger1F2: Weniger's sequence transformation of the ₁F₂, the reference's summation in Double64;
+                              restated at the end of this file on 32-digit mpmath numbers)
+The ₁F₂ of moments.jl:24-27,72-76 is evaluated two ways: by the restated weniger1F2 (the reference's method) and by mpmath's own
+hyp1f2 at 40 digits (an independent evaluation of the same function; this is what the table fill uses, for speed).  The two agree
+to 1e-23 or better, and both are pinned by the reference's own big-float known answers (test/testbessel.jl, every testset), see
 tests/test_bessel_moments.py.
 """
 import math
@@ -281,3 +283,159 @@ def loop_integrate_sph_bessel_filon(f, f1, f2, k, a, b, itp, itp_ka):
     itp_kb = itp(k * b)
     dI = itp_kb - itp_ka
     return (c0 * ki) * dI[0] + (c1 * ki * ki) * dI[1] + (c2 * ki ** 3) * dI[2], itp_kb
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# weniger.jl: the reference's own summation of the 1F2 (Weniger's sequence transformation, 1-based arrays as there)
+# ------------------------------------------------------------------------------------------------------------------
+def weniger1F2(alpha, beta, z, dps=32, kmax=100000):
+    """weniger1F2(α, β::SVector{2}, z, cache) restated (weniger.jl:50-235) with mpmath numbers of `dps` digits standing in for
+    Double64 (~32 digits).  Arrays are 1-based like the reference's (index 0 unused) so that every subscript can be compared with
+    the source.  Used only to show that the reference's summation method and the oracle's 40-digit hyp1f2 agree."""
+    with mpmath.workdps(dps):
+        mpf, rf = mpmath.mpf, mpmath.rf
+        eps = mpf(2) ** (-int(dps * 3.3219))
+        a = mpf(alpha); b = [None, mpf(beta[0]), mpf(beta[1])]; z = mpf(z)
+        if abs(z) < eps:
+            return mpf(1)
+        gam = mpf(3) / 2
+        zeta = 1 / z
+        p, q, r, rho = 1, 2, 5, 3
+
+        def arr(n):
+            return [mpf(0)] * (n + 1)
+        C, Crho, C1, C2, C3, P = arr(r), arr(rho + 2), arr(rho + 1), arr(rho + 2), arr(rho + 2), arr(rho + 2)
+        Q, N, dN, dNold, D, dD, dDold, R = arr(q + 2), arr(r + 1), arr(r + 1), arr(r + 1), arr(r + 1), arr(r + 1), arr(r + 1), arr(r + 1)
+        C[1] = mpf(1)
+        Crho[rho + 2] = mpf(1)
+        for s in range(rho, -1, -1):
+            Crho[s + 1] = -(s + 1) * Crho[s + 2] / (rho + 1 - s)
+        C2[rho + 2] = 1 / rf(gam - rho - 2, rho + 2)
+        C3[rho + 1] = 1 / rf(gam - rho - 1, rho + 2)
+        C3[rho + 2] = 1 / rf(gam - rho, rho + 2)
+        P[1] = gam * (a + 1)
+        err = abs(gam) * (abs(a) + 1)
+        Q[1] = 2 * (b[1] + 1) * (b[2] + 1)
+        N[r + 1] = b[1] * b[2] * zeta / a / (gam - 1)
+        dN[r] = N[r + 1] / rf(gam - rho - 1, rho)
+        D[r + 1] = b[1] * b[2] * zeta / a / (gam - 1)
+        dD[r] = D[r + 1] / rf(gam - rho - 1, rho)
+        R[r + 1] = N[r + 1] / D[r + 1]
+
+        def errcheck(x, y, tol):
+            return mpmath.isfinite(x) and mpmath.isfinite(y) and abs(x - y) > max(abs(x), abs(y)) * tol
+        k = 0
+        while k < r or (k < kmax and errcheck(R[r], R[r + 1], 10 * eps)):
+            for j in range(1, r + 1):
+                N[j], D[j], R[j] = N[j + 1], D[j + 1], R[j + 1]
+            t1 = mpf(0)
+            for j in range(0, min(k, q + 1) + 1):
+                t1 += C[j + 1] * Q[j + 1] * dN[r - j]
+            if k <= rho:
+                for j in range(0, k + 1):
+                    t2 = (b[1] + j + 1) * (b[2] + j + 1) * (j + 2)
+                    t1 += C[j + 1] * mpf(-1) ** (k - j) * rf(j + gam, k - rho - 1) * t2
+            t2 = mpf(0)
+            s2 = mpf(0)
+            for s in range(max(0, rho + 1 - k), rho + 1):
+                s2 += Crho[s + 1] * C1[s + 1] * (N[r - rho + s] + (gam + k - rho + s - 2) * N[r - rho + s - 1])
+            s2 += (gam + k - 1) * N[r] / rf(gam + 2 * k - rho - 1, rho + 2)
+            t2 += P[1] * s2
+            s2 = mpf(0)
+            for s in range(max(0, rho + 1 - k), rho + 2):
+                s2 += Crho[s + 1] * C2[s + 1] * (gam + 2 * k - 2 * rho + 2 * s - 3) * N[r - rho + s - 1]
+            dNold[r + 1] = s2
+            for j in range(1, min(k, p + 1) + 1):
+                t2 += C[j + 1] * P[j + 1] * (dNold[r + 2 - j] + dNold[r + 1 - j])
+            N[r + 1] = zeta * t1 - t2
+            t1 = mpf(0)
+            for j in range(0, min(k, q + 1) + 1):
+                t1 += C[j + 1] * Q[j + 1] * dD[r - j]
+            t2 = mpf(0)
+            s2 = mpf(0)
+            for s in range(max(0, rho + 1 - k), rho + 1):
+                s2 += Crho[s + 1] * C1[s + 1] * (D[r - rho + s] + (gam + k - rho + s - 2) * D[r - rho + s - 1])
+            s2 += (gam + k - 1) * D[r] / rf(gam + 2 * k - rho - 1, rho + 2)
+            t2 += P[1] * s2
+            s2 = mpf(0)
+            for s in range(max(0, rho + 1 - k), rho + 2):
+                s2 += Crho[s + 1] * C2[s + 1] * (gam + 2 * k - 2 * rho + 2 * s - 3) * D[r - rho + s - 1]
+            dDold[r + 1] = s2
+            for j in range(1, min(k, p + 1) + 1):
+                t2 += C[j + 1] * P[j + 1] * (dDold[r + 2 - j] + dDold[r + 1 - j])
+            D[r + 1] = zeta * t1 - t2
+            if abs(P[1]) < eps * err:
+                return N[r + 1] / D[r + 1]
+            sc = P[1] / rf(gam + 2 * k - rho - 1, rho + 2)
+            N[r + 1] /= sc
+            D[r + 1] /= sc
+            R[r + 1] = N[r + 1] / D[r + 1]
+            s1 = mpf(0)
+            for s in range(max(0, rho - k), rho + 2):
+                s1 += Crho[s + 1] * C3[s + 1] * (gam + 2 * k - 2 * rho + 2 * s - 1) * N[r - rho + s]
+            dN[r + 1] = s1
+            s1 = mpf(0)
+            for s in range(max(0, rho - k), rho + 2):
+                s1 += Crho[s + 1] * C3[s + 1] * (gam + 2 * k - 2 * rho + 2 * s - 1) * D[r - rho + s]
+            dD[r + 1] = s1
+            k += 1
+            for j in range(min(k, p + 1), -1, -1):
+                dNold[r - j] = (gam + 2 * k - rho - j - 4) * dNold[r - j + 1] + (k - j - 1) * dNold[r - j]
+            for j in range(min(k, q + 1), -1, -1):
+                dN[r - j] = (gam + 2 * k - rho - j - 2) * dN[r - j + 1] + (k - j) * dN[r - j]
+            for j in range(min(k, p + 1), -1, -1):
+                dDold[r - j] = (gam + 2 * k - rho - j - 4) * dDold[r - j + 1] + (k - j - 1) * dDold[r - j]
+            for j in range(min(k, q + 1), -1, -1):
+                dD[r - j] = (gam + 2 * k - rho - j - 2) * dD[r - j + 1] + (k - j) * dD[r - j]
+            for j in range(min(k, rho), 0, -1):
+                C[j + 1] += C[j]
+            if k <= rho + 1:
+                for s in range(max(0, rho + 1 - k), rho + 1):
+                    C1[s + 1] = rf(k - rho + s, rho + 1 - s) / rf(gam + 2 * k - 2 * rho + s - 2, rho + 2)
+                for s in range(max(0, rho + 1 - k), rho + 2):
+                    C2[s + 1] = rf(k - rho + s, rho + 1 - s) / rf(gam + 2 * k - 2 * rho + s - 3, rho + 2)
+            else:
+                for s in range(0, rho + 1):
+                    C1[s + 1] *= mpf(k) / (k - mpf(1) - rho + s) * (gam + 2 * k - 2 * rho + s - 4) / (gam + 2 * k - rho + s - 2) * \
+                        (gam + 2 * k - 2 * rho + s - 3) / (gam + 2 * k - rho + s - 1)
+                for s in range(0, rho + 2):
+                    C2[s + 1] *= mpf(k) / (k - mpf(1) - rho + s) * (gam + 2 * k - 2 * rho + s - 5) / (gam + 2 * k - rho + s - 3) * \
+                        (gam + 2 * k - 2 * rho + s - 4) / (gam + 2 * k - rho + s - 2)
+            if k <= rho:
+                for s in range(max(0, rho - k), rho + 2):
+                    C3[s + 1] = rf(k - rho + s + 1, rho + 1 - s) / rf(gam + 2 * k - 2 * rho + s - 1, rho + 2)
+            else:
+                for s in range(max(0, rho - k), rho + 2):
+                    C3[s + 1] *= (k + mpf(1)) / (k - rho + s) * (gam + 2 * k - 2 * rho + s - 3) / (gam + 2 * k - rho + s - 1) * \
+                        (gam + 2 * k - 2 * rho + s - 2) / (gam + 2 * k - rho + s)
+            t = (gam + k) * (a + k + 1)
+            err = (abs(gam) + k) * (abs(a) + k + 1)
+            for j in range(2, p + 3):
+                s_ = t - P[j - 1]
+                P[j - 1] = t
+                t = s_
+            P[p + 2] = t
+            t = (b[1] + k + 1) * (b[2] + k + 1) * (k + 2)
+            for j in range(2, q + 3):
+                s_ = t - Q[j - 1]
+                Q[j - 1] = t
+                t = s_
+            Q[q + 2] = t
+        return R[r + 1] if mpmath.isfinite(R[r + 1]) else R[r]
+
+
+def sph_j_moment_weniger_1F2(x, nu, m, dps=32):
+    """sph_j_moment_weniger_₁F₂ (moments.jl:72-76) with the reference's own summation (weniger1F2 above)."""
+    with mpmath.workdps(dps):
+        x = mpmath.mpf(x)
+        nup = nu + mpmath.mpf(3) / 2
+        pre = (1 / mpmath.mpf(m + nu + 1)) * mpmath.exp((m + nu + 1) * mpmath.log(x) - (nup - 1) * mpmath.log(2) - mpmath.loggamma(nup))
+        return pre * weniger1F2(mpmath.mpf(1 + m + nu) / 2, (mpmath.mpf(3 + m + nu) / 2, nup), -x * x / 4, dps) * mpmath.sqrt(mpmath.pi / 2)
+
+
+def J_moment_weniger_1F2(x, nu, alpha, dps=32):
+    """J_moment_weniger_₁F₂ (moments.jl:24-27) with the reference's own summation."""
+    with mpmath.workdps(dps):
+        x, nu, alpha = mpmath.mpf(x), mpmath.mpf(nu), mpmath.mpf(alpha)
+        pre = (1 / (alpha + nu + 1)) * mpmath.exp((alpha + nu + 1) * mpmath.log(x) - nu * mpmath.log(2) - mpmath.loggamma(nu + 1))
+        return pre * weniger1F2((1 + alpha + nu) / 2, ((3 + alpha + nu) / 2, 1 + nu), -x * x / 4, dps)

@@ -136,3 +136,25 @@ def test_filon_third_order(tables):                           # :275-305
     assert abs((F(7494., 299.8, 6., 10.0, 50.0, 100.0, itp) - refs[2]) / refs[2]) < TOL
     assert abs((F(119964., 1199.8, 6., 10., 200., 201., itp) - refs[3]) / refs[3]) < TOL
     assert abs((F(74999004, 149999 / 5, 6., 10., 5000., 5100., itp) - refs[4]) / refs[4]) < TOL
+
+
+def test_restated_weniger_summation_matches_the_known_answers_and_hyp1f2():
+    """The reference's own summation of the 1F2 (weniger.jl:50-235, restated on 32-digit numbers): every known answer the reference
+    checks its Weniger sums against (testbessel.jl:27,40,46,70,83,89,94,118), and agreement with the independent 40-digit hyp1f2
+    over the range the table fill uses it on."""
+    for alpha, ref in zip((0, 1, 2), J_MODERATE):
+        assert rel(O.J_moment_weniger_1F2(200.0, 2.5, alpha), ref) < TOL
+    assert rel(O.J_moment_weniger_1F2(10.0, 2.5, 1.5), big("-0.98904817846028826228408967797229")) < 1e-15
+    assert rel(O.J_moment_weniger_1F2(0.1, 2.5, -0.5), big("0.00001772317062480308")) < TOL
+    for nu, refs in ((2, QUAD_200), (3, OCT_200)):
+        for m, ref in zip((0, 1, 2), refs):
+            assert rel(O.sph_j_moment_weniger_1F2(200.0, nu, m), ref) < TOL
+    assert rel(O.sph_j_moment_weniger_1F2(0.1, 2, 1), big("1.66587318119689113603548520948514e-6")) < TOL
+    assert rel(O.sph_j_moment_weniger_1F2(0.1, 2, 0), big("0.0000222127003021204915961147418458393")) < TOL
+    assert rel(O.sph_j_moment_weniger_1F2(0.01, 2, 2), big("1.33332653062694211665894244946280e-12")) < TOL
+    rng = np.random.default_rng(21)
+    for x in np.concatenate([rng.uniform(0.01, 50.0, 12), [1e-3, 49.99]]):
+        for nu in (2, 3):
+            for m in range(4):
+                a, b = O.sph_j_moment_weniger_1F2(x, nu, m), O.sph_j_moment_1F2(x, nu, m)
+                assert abs(a - b) < 1e-20 * max(abs(b), big(x) ** (m - 1)), (x, nu, m)
