@@ -11,6 +11,13 @@ per GPU.  Multi-GPU: cosmologies shard over ranks with no data-path collective (
   e2e    = same metric through the reference-facing API with HOST buffers: every step uploads the cosmology's
            tables (H2D), runs bolt_spectra and reads C_l back (D2H)
   --impl reference : the oracle port (C++/OpenMP, all host cores) on a bounded sample of the same workload
+  --scaling strong : BASELINE configs[3] (10^4 modes, l_gamma = 50, ONE cosmology) sharded over the GPUs inside the library
+
+Extra objects on the line (never at the cost of the headline: each arm is guarded): `gradients` (the C3 workload with six forward-mode
+partials and its own CPU baseline -- the workload north_star's >= 100x target is quoted on), `plin` (configs[1]), `batch`
+(bolt_spectra_batch), `hostgen` and `params_to_spectra` (input tables of a batch of parameter sets made on the device), `filon`
+(Bessel-moment table + Filon chains, with the numpy oracle as its CPU arm); at N > 1 `strong_scaling` (ONE cosmology sharded inside the
+library with NCCL: bolt_spectra_sharded, bolt_plin_sharded).
 """
 import argparse
 import json
